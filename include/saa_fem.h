@@ -1,0 +1,159 @@
+/*
+ * saa_fem.h — C ABI of the B200-native explicit FE time-step path.
+ *
+ * This is the drop-in boundary for the hot path of desResLab/Synchronization-avoiding-algorithms.
+ * The reference has no FFI: the path sits behind three Python functions (all paths below are
+ * under /root/reference):
+ *
+ *   parallel_explicit_solver_dis_pre(LocalK, F_rankwise, Points, Local_nodes, Local_Dirichlet,
+ *                                    T, Elas, l_M, alpha, size, rank, MODEL)   Tools/Dynamic_solver.py:9-34
+ *   syn_cpus(size, rank, f, L_g, Local_nodes)                                  Tools/Distributed_tools.py:77-92
+ *   Local_assembly_for_stiffness(...) -> scipy csr_matrix                      Tools/Mat_construction.py:122-150
+ *
+ * A maintainer binds the entry points below with ctypes; the Python shims in
+ * synchronization-avoiding-algorithms_b200/Tools/ keep the reference's signatures on top of them.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; every function returns 0 on success, <0 on error;
+ *     saa_last_error() returns a message for the calling thread's last failure.
+ *   - "host" pointers are ordinary CPU memory, "dev" pointers are CUDA device memory on the plan's GPU.
+ *   - A plan belongs to one GPU and one partition (MPI rank of the reference); not thread-safe.
+ *   - All floating-point data is IEEE binary64.  The kernels evaluate every row sum and the update
+ *     formula in the reference's operation order with separately rounded multiply/add (no FMA), so
+ *     results are bit-identical to the reference's numpy/scipy arithmetic.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SAA_FEM_H
+#define SAA_FEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct saa_plan saa_plan;     /* one partition's device-resident problem + state */
+typedef struct saa_group saa_group;   /* several plans of ONE process stepped together (halo exchange by
+                                         device copies) — used to run a P-way partition on fewer GPUs */
+
+/* step modes (MODEL / size arguments of Dynamic_solver.py:9-10,22,25) */
+#define SAA_MODE_LOCAL 0      /* size == 1, or MODEL=True: no exchange, F_int = LocalK.dot(d0)            */
+#define SAA_MODE_SYNC 1       /* size != 1 and MODEL=False: partial forces of shared DOFs are summed over
+                                 their holders in ascending rank order (Distributed_tools.py:83-86)       */
+#define SAA_MODE_PREDICT 2    /* MODEL=True + Online_predictor.py:298: shared DOFs overwritten by rows of
+                                 the prediction table set with saa_plan_set_prediction                    */
+
+/* launch strategies for saa_plan_step / saa_group_step */
+#define SAA_LAUNCH_AUTO 0
+#define SAA_LAUNCH_PER_STEP 1   /* one fused kernel launch per time step                                  */
+#define SAA_LAUNCH_GRAPH 2      /* two-step CUDA graph replayed n/2 times                                 */
+#define SAA_LAUNCH_PERSISTENT 3 /* one cooperative kernel looping over all steps with grid-wide barriers  */
+
+int saa_version(void);
+const char *saa_last_error(void);
+int saa_device_count(void);
+
+/*
+ * Build a plan from the inputs of parallel_explicit_solver_dis_pre (Dynamic_solver.py:9-10):
+ *   n_dof            3 * len(Local_nodes)
+ *   indptr/indices/data   LocalK as scipy CSR (int32 indptr and indices, sorted columns, float64 data).
+ *                    The stored order inside each row is kept: it is the summation order of csr_matvec.
+ *   F_rankwise, l_M  (n_dof) un-ramped load and lumped mass
+ *   dirichlet        Local_Dirichlet: local DOF ids forced to 0 (Dynamic_solver.py:20,32)
+ *   dt               T.dt;  dt2 = T.dt**2, dt_half = T.dt/2, half_alpha = 0.5*alpha are the scalar
+ *                    sub-expressions of Dynamic_solver.py:17 evaluated by the caller in Python (np.float64
+ *                    `**` goes through libm pow) so that the kernel uses the very same constants
+ *   alpha            mass-proportional damping factor (`alpha` argument, Damp in Data_prepare.py:41)
+ * The arrays are copied; the caller may free them afterwards.  State starts at d0 = dn = 0, tn = 0.
+ */
+int saa_plan_create(saa_plan **out, int device, int64_t n_dof, const int32_t *indptr, const int32_t *indices,
+                    const double *data, const double *F_rankwise, const double *l_M, const int64_t *dirichlet,
+                    int64_t n_dirichlet, double dt, double dt2, double dt_half, double half_alpha, double alpha);
+
+/*
+ * Describe the partition interface of this plan (what syn_cpus, Distributed_tools.py:77-92, derives
+ * from rank_local_node_list each step).  Must be called before saa_plan_finalize for size > 1.
+ *   rank, size        this partition and the number of partitions
+ *   n_shared          number of shared nodes of this rank
+ *   shared_pos        (n_shared) their positions in Local_nodes, in the canonical interface order
+ *                     (ascending global node id)
+ *   n_nb, nb_rank     neighbouring ranks, ascending
+ *   nb_ptr            (n_nb+1) offsets into send_idx
+ *   send_idx          for neighbour k: positions (into shared_pos) of the nodes shared with it, ascending
+ *                     global id — the neighbour lists the same nodes in the same order
+ *   holders_ptr       (n_shared+1) CSR over shared nodes
+ *   holders_rank      ranks holding the node, ASCENDING (own rank included)
+ *   holders_slot      -1 for the own rank, else the index of the node inside the message from that rank
+ */
+int saa_plan_set_halo(saa_plan *plan, int rank, int size, int64_t n_shared, const int64_t *shared_pos,
+                      int n_nb, const int32_t *nb_rank, const int64_t *nb_ptr, const int64_t *send_idx,
+                      const int64_t *holders_ptr, const int32_t *holders_rank, const int64_t *holders_slot);
+
+/* Upload everything to the GPU (boundary-first row order, sliced-ELL storage). */
+int saa_plan_finalize(saa_plan *plan);
+int saa_plan_destroy(saa_plan *plan);
+
+/* sizes / layout facts, e.g. for the roofline arithmetic of bench.py */
+int64_t saa_plan_n_dof(const saa_plan *plan);
+int64_t saa_plan_nnz(const saa_plan *plan);           /* stored entries of LocalK                         */
+int64_t saa_plan_padded_entries(const saa_plan *plan);/* entries streamed per step incl. slice padding    */
+int64_t saa_plan_kernel_launches(const saa_plan *plan);/* kernels launched by this plan so far            */
+
+/* State = (d0, dn, tn) of Time_integration_displacement (commons.py:47-52), local DOF order. */
+int saa_plan_set_state(saa_plan *plan, const double *d0_host, const double *dn_host, double tn);
+int saa_plan_get_state(saa_plan *plan, double *d0_host, double *dn_host, double *tn);
+int saa_plan_set_state_dev(saa_plan *plan, const double *d0_dev, const double *dn_dev, double tn);
+int saa_plan_get_state_dev(saa_plan *plan, double *d0_dev, double *dn_dev, double *tn);
+
+/*
+ * n_steps iterations of the loop body of Data_prepare.py:223-235 with the state resident in HBM:
+ *   d1 = step(d0, dn, tn);  dn <- d0;  d0 <- d1;  tn <- tn + dt.
+ * mode SAA_MODE_SYNC needs a transport: a group (saa_group_create) or NCCL (saa_plan_init_nccl).
+ * Work is enqueued on the plan's stream; saa_plan_synchronize waits for it.
+ */
+int saa_plan_step(saa_plan *plan, int64_t n_steps, int mode, int launch);
+int saa_plan_synchronize(saa_plan *plan);
+
+/*
+ * The reference-facing call with HOST buffers: one evaluation of
+ * parallel_explicit_solver_dis_pre(..., T=(tn, dt, d0, dn), ...) -> d1 (Dynamic_solver.py:9-34).
+ * Copies d0 and dn to the GPU, runs one step, copies d1 back; the plan's state becomes (d1, d0, tn+dt).
+ */
+int saa_step_host(saa_plan *plan, const double *d0_host, const double *dn_host, double tn, int mode,
+                  double *d1_host);
+
+/*
+ * Record rows of the solution on the device every `save_every` steps (the d1_save / d_sol_shared
+ * arrays of Data_prepare.py:219,238-240 and Online_predictor.py:244,260,301).
+ *   dofs       local DOF ids to record (NULL: all n_dof), n_dofs their number
+ *   capacity   number of snapshots the device buffer can hold (ring)
+ */
+int saa_plan_set_history(saa_plan *plan, const int64_t *dofs, int64_t n_dofs, int64_t capacity, int64_t save_every);
+int64_t saa_plan_history_count(const saa_plan *plan);
+/* copy snapshots [first, first+count) (snapshot-major, n_dofs values each) to host memory */
+int saa_plan_read_history(saa_plan *plan, int64_t first, int64_t count, double *out_host);
+
+/*
+ * Synchronization-avoiding mode (Online_predictor.py:280-301): `table` holds n_rows predictions of the
+ * shared DOFs, row-major (n_rows, 3*n_shared_ref) in the order of the reference's loc_dof_shared
+ * (`dofs`, local DOF ids, Online_predictor.py:129).  A SAA_MODE_PREDICT step overwrites those DOFs of d1
+ * with the next unread row.
+ */
+int saa_plan_set_prediction(saa_plan *plan, const int64_t *dofs, int64_t n_dofs, const double *table_dev,
+                            int64_t n_rows);
+
+/* ---- several partitions in one process (P ranks on fewer GPUs; exchange by device copies) ---------- */
+int saa_group_create(saa_group **out, saa_plan **plans, int n_plans);
+int saa_group_step(saa_group *grp, int64_t n_steps, int mode, int launch);
+int saa_group_synchronize(saa_group *grp);
+int saa_group_destroy(saa_group *grp);
+
+/* ---- one partition per process / GPU: halo exchange over NCCL (NVLink) -------------------------------- */
+/* 128-byte NCCL unique id, created on one rank and distributed by the caller (torch.distributed) */
+int saa_nccl_unique_id(void *id128);
+int saa_plan_init_nccl(saa_plan *plan, const void *id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAA_FEM_H */

@@ -1,0 +1,820 @@
+// saa_fem.cu — C ABI (include/saa_fem.h) of the explicit FE time-step path: plan construction
+// (boundary-first / sigma-sorted sliced-ELL layout), state movement, stepping strategies (per-step
+// launches, CUDA graph, cooperative persistent loop) and halo transports (in-process group, NCCL).
+//
+// Reference semantics restated here (paths under /root/reference): Tools/Dynamic_solver.py:9-34,
+// Tools/Distributed_tools.py:77-92, Data_prepare.py:223-240, Online_predictor.py:251-318.
+#include "saa_kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/saa_fem.h"
+
+#define SAA_SIGMA 4096          // rows per sorting window (multiple of 32)
+#define SAA_WARPS_PER_BLOCK 8
+
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- minimal NCCL binding resolved at run time (torch ships libnccl.so.2; no link-time dependency) ----
+typedef struct { char internal[128]; } saa_ncclUniqueId;
+typedef void *saa_ncclComm_t;
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(saa_ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(saa_ncclComm_t *, int, saa_ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(saa_ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, saa_ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, saa_ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int SAA_NCCL_DOUBLE = 8;   // ncclFloat64
+
+static int load_nccl()
+{
+    if (g_nccl.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail("cannot dlopen libnccl.so.2 (%s); import torch first or set LD_LIBRARY_PATH", dlerror());
+#define SYM(f, name)                                             \
+    *(void **)(&g_nccl.f) = dlsym(g_nccl.h, name);               \
+    if (!g_nccl.f) return fail("libnccl: missing symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+#define NCK(call)                                                                                        \
+    do {                                                                                                 \
+        int e_ = (call);                                                                                 \
+        if (e_ != 0) return fail("%s:%d %s -> NCCL error %d (%s)", __FILE__, __LINE__, #call, e_,        \
+                                 g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "?");               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+struct saa_plan {
+    int device = 0;
+    bool finalized = false;
+    // host copies of the inputs (released by finalize)
+    int64_t n_dof = 0;
+    std::vector<int32_t> indptr, indices;
+    std::vector<double> data, F, M;
+    std::vector<int64_t> dirichlet;
+    double dt = 0, dt2 = 0, dt_half = 0, half_alpha = 0, alpha = 0;
+    // halo description (host)
+    int rank = 0, size = 1;
+    std::vector<int64_t> shared_pos, nb_ptr, send_idx, holders_ptr, holders_slot;
+    std::vector<int32_t> nb_rank, holders_rank;
+    // layout
+    int64_t nnz = 0, padded_entries = 0, n_rows = 0, n_slices = 0, sh_slices = 0;
+    std::vector<int32_t> iperm_h;          // external local DOF -> internal row
+    // device
+    SaaDev D{};
+    SaaHaloDev H{};
+    int64_t *d_slice_ptr = nullptr;
+    double *d_val = nullptr, *d_M = nullptr, *d_F = nullptr;
+    int32_t *d_col = nullptr, *d_iperm = nullptr;
+    uint32_t *d_dir = nullptr;
+    double *d_buf[2] = {nullptr, nullptr};  // displacement levels; d0 = d_buf[cur], dn = d_buf[cur^1]
+    double *d_tn = nullptr;                 // [2], tn = d_tn[cur]
+    int cur = 0;
+    double *d_stage = nullptr;              // 3*n_dof staging in external order (state I/O)
+    // halo device
+    double *d_xbuf = nullptr, *d_send = nullptr;
+    int64_t *d_dst_ptr = nullptr, *d_src_ptr = nullptr;
+    int32_t *d_dst_pos = nullptr, *d_src_pos = nullptr;
+    std::vector<int64_t> msg_off;           // [n_nb+1] offsets (in doubles) of each neighbour's message
+    int64_t total_msg = 0;
+    // history ring
+    int32_t *d_hist_rows = nullptr;
+    double *d_hist = nullptr;
+    int64_t hist_n = 0, hist_cap = 0, hist_every = 1, hist_count = 0, step_index = 0;
+    // prediction table (sync-avoiding mode)
+    int32_t *d_pred_rows = nullptr;
+    const double *d_pred_table = nullptr;
+    int64_t pred_n = 0, pred_rows = 0, pred_next = 0;
+    // execution
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // LOCAL-mode two-step graphs captured at cur = 0 / 1
+    int coop_blocks = 0;
+    int64_t launches = 0;
+    saa_ncclComm_t comm = nullptr;
+    saa_group *group = nullptr;
+};
+
+struct saa_group {
+    std::vector<saa_plan *> plans;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" int saa_version(void) { return 100; }
+extern "C" const char *saa_last_error(void) { return g_err.c_str(); }
+extern "C" int saa_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int saa_plan_create(saa_plan **out, int device, int64_t n_dof, const int32_t *indptr, const int32_t *indices,
+                               const double *data, const double *F_rankwise, const double *l_M,
+                               const int64_t *dirichlet, int64_t n_dirichlet, double dt, double dt2, double dt_half,
+                               double half_alpha, double alpha)
+{
+    if (!out || n_dof <= 0 || !indptr || !indices || !data || !F_rankwise || !l_M)
+        return fail("saa_plan_create: null or empty argument");
+    if (n_dof % 3 != 0) return fail("saa_plan_create: n_dof=%lld is not a multiple of 3", (long long)n_dof);
+    if (n_dirichlet > 0 && !dirichlet) return fail("saa_plan_create: dirichlet is null");
+    if (saa_device_count() <= device) return fail("saa_plan_create: CUDA device %d not available (no CPU fallback)", device);
+    const int64_t nnz = indptr[n_dof];
+    for (int64_t i = 0; i < n_dof; ++i)
+        if (indptr[i + 1] < indptr[i]) return fail("saa_plan_create: indptr not monotone at row %lld", (long long)i);
+    for (int64_t k = 0; k < nnz; ++k)
+        if (indices[k] < 0 || indices[k] >= n_dof) return fail("saa_plan_create: column index out of range at %lld", (long long)k);
+    for (int64_t k = 0; k < n_dirichlet; ++k)
+        if (dirichlet[k] < 0 || dirichlet[k] >= n_dof) return fail("saa_plan_create: Dirichlet DOF out of range");
+    saa_plan *p = new saa_plan();
+    p->device = device;
+    p->n_dof = n_dof;
+    p->indptr.assign(indptr, indptr + n_dof + 1);
+    p->indices.assign(indices, indices + nnz);
+    p->data.assign(data, data + nnz);
+    p->F.assign(F_rankwise, F_rankwise + n_dof);
+    p->M.assign(l_M, l_M + n_dof);
+    p->dirichlet.assign(dirichlet, dirichlet + n_dirichlet);
+    p->dt = dt; p->dt2 = dt2; p->dt_half = dt_half; p->half_alpha = half_alpha; p->alpha = alpha;
+    p->nnz = nnz;
+    *out = p;
+    return 0;
+}
+
+extern "C" int saa_plan_set_halo(saa_plan *p, int rank, int size, int64_t n_shared, const int64_t *shared_pos, int n_nb,
+                                 const int32_t *nb_rank, const int64_t *nb_ptr, const int64_t *send_idx,
+                                 const int64_t *holders_ptr, const int32_t *holders_rank, const int64_t *holders_slot)
+{
+    if (!p) return fail("saa_plan_set_halo: null plan");
+    if (p->finalized) return fail("saa_plan_set_halo: plan already finalized");
+    if (rank < 0 || rank >= size) return fail("saa_plan_set_halo: bad rank %d of %d", rank, size);
+    p->rank = rank; p->size = size;
+    if (n_shared > 0) {
+        if (!shared_pos || !nb_rank || !nb_ptr || !send_idx || !holders_ptr || !holders_rank || !holders_slot || n_nb <= 0)
+            return fail("saa_plan_set_halo: null argument");
+        for (int64_t j = 0; j < n_shared; ++j)
+            if (shared_pos[j] < 0 || 3 * shared_pos[j] + 2 >= p->n_dof) return fail("saa_plan_set_halo: shared_pos out of range");
+        p->shared_pos.assign(shared_pos, shared_pos + n_shared);
+        p->nb_rank.assign(nb_rank, nb_rank + n_nb);
+        p->nb_ptr.assign(nb_ptr, nb_ptr + n_nb + 1);
+        p->send_idx.assign(send_idx, send_idx + nb_ptr[n_nb]);
+        p->holders_ptr.assign(holders_ptr, holders_ptr + n_shared + 1);
+        p->holders_rank.assign(holders_rank, holders_rank + holders_ptr[n_shared]);
+        p->holders_slot.assign(holders_slot, holders_slot + holders_ptr[n_shared]);
+        for (int64_t k = 0; k < nb_ptr[n_nb]; ++k)
+            if (send_idx[k] < 0 || send_idx[k] >= n_shared) return fail("saa_plan_set_halo: send_idx out of range");
+    }
+    return 0;
+}
+
+template <class T>
+static int upload(T **dptr, const std::vector<T> &h)
+{
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CK(cudaMalloc((void **)dptr, bytes));
+    if (!h.empty()) CK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// order rows of one region: windows of SAA_SIGMA rows sorted by decreasing length (stable)
+static void sigma_sort(std::vector<int64_t> &rows, const std::vector<int32_t> &indptr)
+{
+    for (size_t w = 0; w < rows.size(); w += SAA_SIGMA) {
+        size_t e = std::min(rows.size(), w + (size_t)SAA_SIGMA);
+        std::stable_sort(rows.begin() + w, rows.begin() + e, [&](int64_t a, int64_t b) {
+            return (indptr[a + 1] - indptr[a]) > (indptr[b + 1] - indptr[b]);
+        });
+    }
+}
+
+extern "C" int saa_plan_finalize(saa_plan *p)
+{
+    if (!p) return fail("saa_plan_finalize: null plan");
+    if (p->finalized) return 0;
+    CK(cudaSetDevice(p->device));
+    const int64_t n = p->n_dof;
+    const int64_t n_shared = (int64_t)p->shared_pos.size();
+
+    // 1. internal row order: shared DOFs (canonical interface order), then the rest ascending
+    std::vector<char> is_shared(n, 0);
+    std::vector<int64_t> sh_rows, in_rows;
+    sh_rows.reserve(3 * n_shared);
+    for (int64_t j = 0; j < n_shared; ++j)
+        for (int c = 0; c < 3; ++c) {
+            int64_t r = 3 * p->shared_pos[j] + c;
+            if (is_shared[r]) return fail("saa_plan_finalize: duplicate shared node");
+            is_shared[r] = 1;
+            sh_rows.push_back(r);
+        }
+    in_rows.reserve(n - sh_rows.size());
+    for (int64_t r = 0; r < n; ++r)
+        if (!is_shared[r]) in_rows.push_back(r);
+    sigma_sort(sh_rows, p->indptr);
+    sigma_sort(in_rows, p->indptr);
+    auto pad32 = [](int64_t v) { return (v + 31) / 32 * 32; };
+    const int64_t sh_pad = pad32((int64_t)sh_rows.size());
+    const int64_t in_pad = pad32((int64_t)in_rows.size());
+    p->n_rows = sh_pad + in_pad;
+    p->n_slices = p->n_rows / 32;
+    p->sh_slices = sh_pad / 32;
+    if (p->n_rows >= (int64_t)INT32_MAX) return fail("saa_plan_finalize: more than 2^31 rows per partition not supported");
+    std::vector<int64_t> perm(p->n_rows, -1);           // internal -> external (-1: padding row)
+    for (size_t i = 0; i < sh_rows.size(); ++i) perm[i] = sh_rows[i];
+    for (size_t i = 0; i < in_rows.size(); ++i) perm[sh_pad + i] = in_rows[i];
+    p->iperm_h.assign(n, -1);
+    for (int64_t i = 0; i < p->n_rows; ++i)
+        if (perm[i] >= 0) p->iperm_h[perm[i]] = (int32_t)i;
+
+    // 2. sliced ELL
+    std::vector<int64_t> slice_ptr(p->n_slices + 1, 0);
+    for (int64_t s = 0; s < p->n_slices; ++s) {
+        int32_t mx = 0;
+        for (int l = 0; l < 32; ++l) {
+            int64_t r = perm[s * 32 + l];
+            if (r >= 0) mx = std::max(mx, p->indptr[r + 1] - p->indptr[r]);
+        }
+        slice_ptr[s + 1] = slice_ptr[s] + 32 * (int64_t)mx;
+    }
+    p->padded_entries = slice_ptr[p->n_slices];
+    std::vector<double> val(p->padded_entries, 0.0);
+    std::vector<int32_t> col(p->padded_entries);
+    for (int64_t s = 0; s < p->n_slices; ++s) {
+        const int64_t len = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
+        for (int l = 0; l < 32; ++l) {
+            const int64_t irow = s * 32 + l;
+            const int64_t r = perm[irow];
+            int64_t cnt = 0;
+            if (r >= 0) {
+                cnt = p->indptr[r + 1] - p->indptr[r];
+                for (int64_t j = 0; j < cnt; ++j) {      // stored order kept: it is the summation order
+                    val[slice_ptr[s] + 32 * j + l] = p->data[p->indptr[r] + j];
+                    col[slice_ptr[s] + 32 * j + l] = p->iperm_h[p->indices[p->indptr[r] + j]];
+                }
+            }
+            // padding: 0.0 * d0[own row] added at the end of the row leaves the sum unchanged
+            for (int64_t j = cnt; j < len; ++j) col[slice_ptr[s] + 32 * j + l] = (int32_t)irow;
+        }
+    }
+    std::vector<double> M(p->n_rows, 1.0), F(p->n_rows, 0.0);
+    for (int64_t i = 0; i < p->n_rows; ++i)
+        if (perm[i] >= 0) { M[i] = p->M[perm[i]]; F[i] = p->F[perm[i]]; }
+    std::vector<uint32_t> dir(p->n_slices, 0u);
+    for (int64_t k : p->dirichlet) {
+        int32_t i = p->iperm_h[k];
+        dir[i >> 5] |= (1u << (i & 31));
+    }
+
+    if (upload(&p->d_slice_ptr, slice_ptr) || upload(&p->d_val, val) || upload(&p->d_col, col) ||
+        upload(&p->d_M, M) || upload(&p->d_F, F) || upload(&p->d_dir, dir) || upload(&p->d_iperm, p->iperm_h))
+        return -1;
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc((void **)&p->d_buf[b], p->n_rows * sizeof(double)));
+        CK(cudaMemset(p->d_buf[b], 0, p->n_rows * sizeof(double)));
+    }
+    CK(cudaMalloc((void **)&p->d_tn, 2 * sizeof(double)));
+    CK(cudaMemset(p->d_tn, 0, 2 * sizeof(double)));
+    CK(cudaMalloc((void **)&p->d_stage, 3 * n * sizeof(double)));
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+
+    p->D.n_rows = p->n_rows; p->D.n_slices = p->n_slices; p->D.sh_slices = p->sh_slices;
+    p->D.slice_ptr = p->d_slice_ptr; p->D.val = p->d_val; p->D.col = p->d_col; p->D.dir_mask = p->d_dir;
+    p->D.M = p->d_M; p->D.F = p->d_F;
+    p->D.dt = p->dt; p->D.dt2 = p->dt2; p->D.dt_half = p->dt_half; p->D.half_alpha = p->half_alpha; p->D.alpha = p->alpha;
+
+    // 3. halo: message layout, pack lists, rank-ordered source lists
+    if (n_shared > 0) {
+        const int n_nb = (int)p->nb_rank.size();
+        p->msg_off.assign(n_nb + 1, 0);
+        for (int k = 0; k < n_nb; ++k) p->msg_off[k + 1] = p->msg_off[k] + 3 * (p->nb_ptr[k + 1] - p->nb_ptr[k]);
+        p->total_msg = p->msg_off[n_nb];
+        if (sh_pad + p->total_msg >= (int64_t)INT32_MAX) return fail("halo too large");
+        // internal row of (shared node j, component c)
+        auto irow = [&](int64_t j, int c) { return (int64_t)p->iperm_h[3 * p->shared_pos[j] + c]; };
+        std::vector<std::vector<int32_t>> dst(sh_pad), src(sh_pad);
+        for (int k = 0; k < n_nb; ++k)
+            for (int64_t e = p->nb_ptr[k]; e < p->nb_ptr[k + 1]; ++e)
+                for (int c = 0; c < 3; ++c)
+                    dst[irow(p->send_idx[e], c)].push_back((int32_t)(p->msg_off[k] + 3 * (e - p->nb_ptr[k]) + c));
+        for (int64_t j = 0; j < n_shared; ++j)
+            for (int64_t h = p->holders_ptr[j]; h < p->holders_ptr[j + 1]; ++h) {
+                if (h > p->holders_ptr[j] && p->holders_rank[h] <= p->holders_rank[h - 1])
+                    return fail("saa_plan_finalize: holders of a shared node must be in ascending rank order");
+                for (int c = 0; c < 3; ++c) {
+                    if (p->holders_slot[h] < 0) {
+                        src[irow(j, c)].push_back((int32_t)irow(j, c));
+                    } else {
+                        int k = (int)(std::find(p->nb_rank.begin(), p->nb_rank.end(), p->holders_rank[h]) - p->nb_rank.begin());
+                        if (k >= n_nb) return fail("saa_plan_finalize: holder rank %d is not a neighbour", p->holders_rank[h]);
+                        if (p->holders_slot[h] >= p->nb_ptr[k + 1] - p->nb_ptr[k]) return fail("holder slot out of range");
+                        src[irow(j, c)].push_back((int32_t)(sh_pad + p->msg_off[k] + 3 * p->holders_slot[h] + c));
+                    }
+                }
+            }
+        std::vector<int64_t> dst_ptr(sh_pad + 1, 0), src_ptr(sh_pad + 1, 0);
+        std::vector<int32_t> dst_pos, src_pos;
+        for (int64_t r = 0; r < sh_pad; ++r) {
+            dst_pos.insert(dst_pos.end(), dst[r].begin(), dst[r].end());
+            src_pos.insert(src_pos.end(), src[r].begin(), src[r].end());
+            dst_ptr[r + 1] = (int64_t)dst_pos.size();
+            src_ptr[r + 1] = (int64_t)src_pos.size();
+        }
+        if (upload(&p->d_dst_ptr, dst_ptr) || upload(&p->d_dst_pos, dst_pos) || upload(&p->d_src_ptr, src_ptr) ||
+            upload(&p->d_src_pos, src_pos))
+            return -1;
+        CK(cudaMalloc((void **)&p->d_xbuf, (sh_pad + p->total_msg) * sizeof(double)));
+        CK(cudaMemset(p->d_xbuf, 0, (sh_pad + p->total_msg) * sizeof(double)));
+        CK(cudaMalloc((void **)&p->d_send, std::max<int64_t>(p->total_msg, 1) * sizeof(double)));
+        p->H.sh_rows = sh_pad; p->H.xbuf = p->d_xbuf; p->H.sendbuf = p->d_send;
+        p->H.dst_ptr = p->d_dst_ptr; p->H.dst_pos = p->d_dst_pos; p->H.src_ptr = p->d_src_ptr; p->H.src_pos = p->d_src_pos;
+    }
+
+    // cooperative launch geometry for the persistent kernel
+    int dev_sms = 0, occ = 0;
+    CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, p->device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, saa_k_persistent, 32 * SAA_WARPS_PER_BLOCK, 0));
+    p->coop_blocks = dev_sms * occ;
+
+    // host copies are no longer needed
+    std::vector<int32_t>().swap(p->indptr); std::vector<int32_t>().swap(p->indices);
+    std::vector<double>().swap(p->data); std::vector<double>().swap(p->F); std::vector<double>().swap(p->M);
+    p->finalized = true;
+    return 0;
+}
+
+extern "C" int saa_plan_destroy(saa_plan *p)
+{
+    if (!p) return 0;
+    if (p->finalized) {
+        cudaSetDevice(p->device);
+        if (p->stream) cudaStreamSynchronize(p->stream);
+        for (int i = 0; i < 2; ++i)
+            if (p->graph_exec[i]) cudaGraphExecDestroy(p->graph_exec[i]);
+        void *ptrs[] = {p->d_slice_ptr, p->d_val, p->d_col, p->d_M, p->d_F, p->d_dir, p->d_iperm, p->d_buf[0], p->d_buf[1],
+                        p->d_tn, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
+                        p->d_hist_rows, p->d_hist, p->d_pred_rows};
+        for (void *q : ptrs)
+            if (q) cudaFree(q);
+        if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+        if (p->stream) cudaStreamDestroy(p->stream);
+    }
+    delete p;
+    return 0;
+}
+
+extern "C" int64_t saa_plan_n_dof(const saa_plan *p) { return p ? p->n_dof : -1; }
+extern "C" int64_t saa_plan_nnz(const saa_plan *p) { return p ? p->nnz : -1; }
+extern "C" int64_t saa_plan_padded_entries(const saa_plan *p) { return p ? p->padded_entries : -1; }
+extern "C" int64_t saa_plan_kernel_launches(const saa_plan *p) { return p ? p->launches : -1; }
+
+static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+#define NEED_FINAL(p, name)                                   \
+    if (!(p)) return fail(name ": null plan");                \
+    if (!(p)->finalized) return fail(name ": plan not finalized")
+
+static int set_state_from_stage(saa_plan *p, cudaStream_t st, double tn)
+{
+    // d_stage holds [d0_ext | dn_ext]; padding rows of the internal buffers stay 0
+    saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage, p->d_buf[p->cur]);
+    saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage + p->n_dof, p->d_buf[p->cur ^ 1]);
+    p->launches += 2;
+    CK(cudaMemcpyAsync(p->d_tn + p->cur, &tn, sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int saa_plan_set_state(saa_plan *p, const double *d0, const double *dn, double tn)
+{
+    NEED_FINAL(p, "saa_plan_set_state");
+    if (!d0 || !dn) return fail("saa_plan_set_state: null argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (set_state_from_stage(p, p->stream, tn)) return -1;
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int saa_plan_set_state_dev(saa_plan *p, const double *d0, const double *dn, double tn)
+{
+    NEED_FINAL(p, "saa_plan_set_state_dev");
+    if (!d0 || !dn) return fail("saa_plan_set_state_dev: null argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (set_state_from_stage(p, p->stream, tn)) return -1;
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+static int get_state_to_stage(saa_plan *p, cudaStream_t st, bool want_d0, bool want_dn)
+{
+    if (want_d0) { saa_k_gather_to_external<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_buf[p->cur], p->d_stage); p->launches++; }
+    if (want_dn) { saa_k_gather_to_external<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_buf[p->cur ^ 1], p->d_stage + p->n_dof); p->launches++; }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int saa_plan_get_state(saa_plan *p, double *d0, double *dn, double *tn)
+{
+    NEED_FINAL(p, "saa_plan_get_state");
+    CK(cudaSetDevice(p->device));
+    if (get_state_to_stage(p, p->stream, d0 != nullptr, dn != nullptr)) return -1;
+    if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int saa_plan_get_state_dev(saa_plan *p, double *d0, double *dn, double *tn)
+{
+    NEED_FINAL(p, "saa_plan_get_state_dev");
+    CK(cudaSetDevice(p->device));
+    if (get_state_to_stage(p, p->stream, d0 != nullptr, dn != nullptr)) return -1;
+    if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ---- history / prediction ------------------------------------------------------------------------------
+extern "C" int saa_plan_set_history(saa_plan *p, const int64_t *dofs, int64_t n_dofs, int64_t capacity, int64_t save_every)
+{
+    NEED_FINAL(p, "saa_plan_set_history");
+    CK(cudaSetDevice(p->device));
+    if (p->d_hist_rows) { cudaFree(p->d_hist_rows); p->d_hist_rows = nullptr; }
+    if (p->d_hist) { cudaFree(p->d_hist); p->d_hist = nullptr; }
+    p->hist_n = p->hist_cap = p->hist_count = 0;
+    if (capacity <= 0) return 0;
+    if (save_every <= 0) return fail("saa_plan_set_history: save_every must be positive");
+    if (!dofs) n_dofs = p->n_dof;
+    std::vector<int32_t> rows(n_dofs);
+    for (int64_t i = 0; i < n_dofs; ++i) {
+        int64_t d = dofs ? dofs[i] : i;
+        if (d < 0 || d >= p->n_dof) return fail("saa_plan_set_history: DOF out of range");
+        rows[i] = p->iperm_h[d];
+    }
+    if (upload(&p->d_hist_rows, rows)) return -1;
+    CK(cudaMalloc((void **)&p->d_hist, (size_t)capacity * n_dofs * sizeof(double)));
+    p->hist_n = n_dofs; p->hist_cap = capacity; p->hist_every = save_every;
+    return 0;
+}
+extern "C" int64_t saa_plan_history_count(const saa_plan *p) { return p ? p->hist_count : -1; }
+extern "C" int saa_plan_read_history(saa_plan *p, int64_t first, int64_t count, double *out)
+{
+    NEED_FINAL(p, "saa_plan_read_history");
+    if (first < 0 || count < 0 || first + count > p->hist_count) return fail("saa_plan_read_history: range out of bounds");
+    if (first < p->hist_count - p->hist_cap) return fail("saa_plan_read_history: snapshots already overwritten");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int64_t s = 0; s < count; ++s) {
+        const int64_t slot = (first + s) % p->hist_cap;
+        CK(cudaMemcpy(out + s * p->hist_n, p->d_hist + slot * p->hist_n, p->hist_n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int saa_plan_set_prediction(saa_plan *p, const int64_t *dofs, int64_t n_dofs, const double *table_dev, int64_t n_rows)
+{
+    NEED_FINAL(p, "saa_plan_set_prediction");
+    CK(cudaSetDevice(p->device));
+    if (dofs) {
+        if (p->d_pred_rows) { cudaFree(p->d_pred_rows); p->d_pred_rows = nullptr; }
+        std::vector<int32_t> rows(n_dofs);
+        for (int64_t i = 0; i < n_dofs; ++i) {
+            if (dofs[i] < 0 || dofs[i] >= p->n_dof) return fail("saa_plan_set_prediction: DOF out of range");
+            rows[i] = p->iperm_h[dofs[i]];
+        }
+        if (upload(&p->d_pred_rows, rows)) return -1;
+        p->pred_n = n_dofs;
+    } else if (n_dofs != p->pred_n) {
+        return fail("saa_plan_set_prediction: n_dofs changed without a DOF list");
+    }
+    p->d_pred_table = table_dev; p->pred_rows = n_rows; p->pred_next = 0;
+    return 0;
+}
+
+// after a step: the new d0 is d_buf[cur]
+static int after_step(saa_plan *p, cudaStream_t st, int mode)
+{
+    if (mode == SAA_MODE_PREDICT) {
+        if (!p->d_pred_table || p->pred_next >= p->pred_rows) return fail("SAA_MODE_PREDICT: prediction table exhausted or not set");
+        // Online_predictor.py:298 — d1[loc_dof_shared] = d_shared[row]
+        saa_k_scatter_rows<<<nblk(p->pred_n, 256), 256, 0, st>>>(p->pred_n, p->d_pred_rows, p->d_pred_table + p->pred_next * p->pred_n, p->d_buf[p->cur]);
+        p->launches++; p->pred_next++;
+    }
+    if (p->hist_cap > 0 && (p->step_index % p->hist_every) == 0) {      // Data_prepare.py:238-240
+        const int64_t slot = p->hist_count % p->hist_cap;
+        saa_k_gather_rows<<<nblk(p->hist_n, 256), 256, 0, st>>>(p->hist_n, p->d_hist_rows, p->d_buf[p->cur], p->d_hist + slot * p->hist_n);
+        p->launches++; p->hist_count++;
+    }
+    p->step_index++;
+    return 0;
+}
+
+// ---- stepping --------------------------------------------------------------------------------------------
+static void launch_local_step(saa_plan *p, cudaStream_t st)
+{
+    saa_k_step<false><<<nblk(p->n_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
+        p->D, 0, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_tn + p->cur, p->d_tn + (p->cur ^ 1));
+    p->cur ^= 1;
+    p->launches++;
+}
+
+static bool needs_hooks(const saa_plan *p, int mode) { return mode == SAA_MODE_PREDICT || p->hist_cap > 0; }
+
+static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
+{
+    cudaStream_t st = p->stream;
+    const bool hooks = needs_hooks(p, mode);
+    if (launch == SAA_LAUNCH_AUTO) launch = hooks ? SAA_LAUNCH_PER_STEP : (n_steps >= 8 ? SAA_LAUNCH_GRAPH : SAA_LAUNCH_PER_STEP);
+    if (hooks && launch != SAA_LAUNCH_PER_STEP) return fail("history / prediction hooks need SAA_LAUNCH_PER_STEP");
+    if (launch == SAA_LAUNCH_PERSISTENT) {
+        if (p->coop_blocks <= 0) return fail("cooperative launch not available");
+        double *a = p->d_buf[p->cur], *b = p->d_buf[p->cur ^ 1], *tn = p->d_tn + p->cur;
+        int64_t ns = n_steps;
+        void *args[] = {&p->D, &a, &b, &tn, &ns};
+        int64_t want = (p->n_slices + SAA_WARPS_PER_BLOCK - 1) / SAA_WARPS_PER_BLOCK;
+        int blocks = (int)std::min<int64_t>(p->coop_blocks, want);
+        CK(cudaLaunchCooperativeKernel((void *)saa_k_persistent, dim3(blocks), dim3(32 * SAA_WARPS_PER_BLOCK), args, 0, st));
+        p->launches++;
+        if (n_steps & 1) {   // an odd number of steps swaps the buffer roles; tn was written back to d_tn[cur]
+            CK(cudaMemcpyAsync(p->d_tn + (p->cur ^ 1), p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            p->cur ^= 1;
+        }
+        p->step_index += n_steps;
+        return 0;
+    }
+    int64_t done = 0;
+    if (launch == SAA_LAUNCH_GRAPH && n_steps >= 2) {
+        const int c = p->cur;
+        if (!p->graph_exec[c]) {
+            cudaGraph_t g;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int64_t l0 = p->launches;
+            launch_local_step(p, st);
+            launch_local_step(p, st);
+            p->launches = l0;
+            CK(cudaStreamEndCapture(st, &g));
+            CK(cudaGraphInstantiate(&p->graph_exec[c], g, 0));
+            CK(cudaGraphDestroy(g));
+        }
+        for (; done + 2 <= n_steps; done += 2) {
+            CK(cudaGraphLaunch(p->graph_exec[c], st));
+            p->launches += 2;
+        }
+        p->step_index += done;
+    }
+    for (; done < n_steps; ++done) {
+        launch_local_step(p, st);
+        if (after_step(p, st, mode)) return -1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// one synchronised step of one plan, split in its three phases so that transports can interleave
+static void sync_phase_boundary(saa_plan *p, cudaStream_t st)
+{
+    if (p->sh_slices > 0) {
+        saa_k_boundary<<<nblk(p->sh_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(p->D, p->H, p->d_buf[p->cur]);
+        p->launches++;
+    }
+}
+static void sync_phase_interior(saa_plan *p, cudaStream_t st)
+{
+    // also advances tn; runs even with zero interior slices so that tn moves
+    const int64_t n_in = p->n_slices - p->sh_slices;
+    saa_k_step<true><<<std::max(1u, nblk(n_in, SAA_WARPS_PER_BLOCK)), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
+        p->D, p->sh_slices, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_tn + p->cur, p->d_tn + (p->cur ^ 1));
+    p->launches++;
+}
+static void sync_phase_shared(saa_plan *p, cudaStream_t st)
+{
+    if (p->sh_slices > 0) {
+        saa_k_shared_update<<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_tn + p->cur);
+        p->launches++;
+    }
+    p->cur ^= 1;
+}
+
+static int step_sync_nccl(saa_plan *p, int64_t n_steps)
+{
+    cudaStream_t st = p->stream;
+    const int n_nb = (int)p->nb_rank.size();
+    for (int64_t s = 0; s < n_steps; ++s) {
+        sync_phase_boundary(p, st);
+        if (n_nb > 0) {
+            NCK(g_nccl.GroupStart());
+            for (int k = 0; k < n_nb; ++k) {
+                const size_t cnt = (size_t)(p->msg_off[k + 1] - p->msg_off[k]);
+                NCK(g_nccl.Send(p->d_send + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
+                NCK(g_nccl.Recv(p->d_xbuf + p->H.sh_rows + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
+            }
+            NCK(g_nccl.GroupEnd());
+        }
+        sync_phase_interior(p, st);
+        sync_phase_shared(p, st);
+        if (after_step(p, st, SAA_MODE_SYNC)) return -1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int saa_plan_step(saa_plan *p, int64_t n_steps, int mode, int launch)
+{
+    NEED_FINAL(p, "saa_plan_step");
+    if (n_steps < 0) return fail("saa_plan_step: negative n_steps");
+    if (n_steps == 0) return 0;
+    CK(cudaSetDevice(p->device));
+    if (mode == SAA_MODE_LOCAL || mode == SAA_MODE_PREDICT) return step_local(p, n_steps, mode, launch);
+    if (mode == SAA_MODE_SYNC) {
+        if (p->size == 1) return step_local(p, n_steps, SAA_MODE_LOCAL, launch);   // Dynamic_solver.py:25 `if size != 1`
+        if (p->group) return fail("saa_plan_step: this plan belongs to a group; use saa_group_step");
+        if (!p->comm) return fail("saa_plan_step: SAA_MODE_SYNC needs a transport (saa_plan_init_nccl or saa_group_create)");
+        return step_sync_nccl(p, n_steps);
+    }
+    return fail("saa_plan_step: unknown mode %d", mode);
+}
+
+extern "C" int saa_plan_synchronize(saa_plan *p)
+{
+    NEED_FINAL(p, "saa_plan_synchronize");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int saa_step_host(saa_plan *p, const double *d0, const double *dn, double tn, int mode, double *d1)
+{
+    NEED_FINAL(p, "saa_step_host");
+    if (!d0 || !dn || !d1) return fail("saa_step_host: null argument");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->group ? p->group->stream : p->stream;
+    if (p->group) return fail("saa_step_host: plan belongs to a group");
+    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (set_state_from_stage(p, st, tn)) return -1;
+    if (saa_plan_step(p, 1, mode, SAA_LAUNCH_PER_STEP)) return -1;
+    if (get_state_to_stage(p, st, true, false)) return -1;
+    CK(cudaMemcpyAsync(d1, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- group transport: P partitions in one process, messages moved by device-to-device copies ------------
+extern "C" int saa_group_create(saa_group **out, saa_plan **plans, int n_plans)
+{
+    if (!out || !plans || n_plans <= 0) return fail("saa_group_create: bad arguments");
+    for (int i = 0; i < n_plans; ++i) {
+        if (!plans[i] || !plans[i]->finalized) return fail("saa_group_create: plan %d is not finalized", i);
+        if (plans[i]->size != n_plans || plans[i]->rank != i) return fail("saa_group_create: plan %d has rank %d of %d", i, plans[i]->rank, plans[i]->size);
+        if (plans[i]->device != plans[0]->device) return fail("saa_group_create: all plans of a group must live on one device");
+    }
+    // message sizes must match pairwise
+    for (int i = 0; i < n_plans; ++i) {
+        saa_plan *a = plans[i];
+        for (size_t k = 0; k < a->nb_rank.size(); ++k) {
+            saa_plan *b = plans[a->nb_rank[k]];
+            auto it = std::find(b->nb_rank.begin(), b->nb_rank.end(), i);
+            if (it == b->nb_rank.end()) return fail("saa_group_create: rank %d lists %d as neighbour but not vice versa", i, a->nb_rank[k]);
+            size_t kk = it - b->nb_rank.begin();
+            if (b->msg_off[kk + 1] - b->msg_off[kk] != a->msg_off[k + 1] - a->msg_off[k])
+                return fail("saa_group_create: interface %d<->%d has different sizes on the two sides", i, a->nb_rank[k]);
+        }
+    }
+    saa_group *g = new saa_group();
+    g->plans.assign(plans, plans + n_plans);
+    CK(cudaSetDevice(plans[0]->device));
+    CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < n_plans; ++i) plans[i]->group = g;
+    *out = g;
+    return 0;
+}
+
+extern "C" int saa_group_step(saa_group *g, int64_t n_steps, int mode, int launch)
+{
+    if (!g) return fail("saa_group_step: null group");
+    (void)launch;
+    CK(cudaSetDevice(g->plans[0]->device));
+    cudaStream_t st = g->stream;
+    // make sure earlier work on the plans' own streams (state uploads) is complete
+    for (saa_plan *p : g->plans) CK(cudaStreamSynchronize(p->stream));
+    for (int64_t s = 0; s < n_steps; ++s) {
+        if (mode == SAA_MODE_SYNC && g->plans.size() > 1) {
+            for (saa_plan *p : g->plans) sync_phase_boundary(p, st);
+            for (size_t i = 0; i < g->plans.size(); ++i) {
+                saa_plan *a = g->plans[i];
+                for (size_t k = 0; k < a->nb_rank.size(); ++k) {
+                    saa_plan *b = g->plans[a->nb_rank[k]];
+                    size_t kk = std::find(b->nb_rank.begin(), b->nb_rank.end(), (int32_t)i) - b->nb_rank.begin();
+                    // a receives from b the message b packed for a
+                    CK(cudaMemcpyAsync(a->d_xbuf + a->H.sh_rows + a->msg_off[k], b->d_send + b->msg_off[kk],
+                                       (a->msg_off[k + 1] - a->msg_off[k]) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                }
+            }
+            for (saa_plan *p : g->plans) {
+                sync_phase_interior(p, st);
+                sync_phase_shared(p, st);
+                if (after_step(p, st, mode)) return -1;
+            }
+        } else {
+            for (saa_plan *p : g->plans) {
+                launch_local_step(p, st);
+                if (after_step(p, st, mode == SAA_MODE_SYNC ? SAA_MODE_LOCAL : mode)) return -1;
+            }
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int saa_group_synchronize(saa_group *g)
+{
+    if (!g) return fail("saa_group_synchronize: null group");
+    CK(cudaSetDevice(g->plans[0]->device));
+    CK(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+
+extern "C" int saa_group_destroy(saa_group *g)
+{
+    if (!g) return 0;
+    cudaSetDevice(g->plans[0]->device);
+    cudaStreamSynchronize(g->stream);
+    for (saa_plan *p : g->plans) p->group = nullptr;
+    cudaStreamDestroy(g->stream);
+    delete g;
+    return 0;
+}
+
+// ---- NCCL transport -----------------------------------------------------------------------------------------
+extern "C" int saa_nccl_unique_id(void *id128)
+{
+    if (!id128) return fail("saa_nccl_unique_id: null argument");
+    if (load_nccl()) return -1;
+    saa_ncclUniqueId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+extern "C" int saa_plan_init_nccl(saa_plan *p, const void *id128)
+{
+    NEED_FINAL(p, "saa_plan_init_nccl");
+    if (!id128) return fail("saa_plan_init_nccl: null id");
+    if (load_nccl()) return -1;
+    CK(cudaSetDevice(p->device));
+    saa_ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NCK(g_nccl.CommInitRank(&p->comm, p->size, id, p->rank));
+    return 0;
+}

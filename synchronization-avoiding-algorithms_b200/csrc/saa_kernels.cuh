@@ -1,0 +1,220 @@
+// saa_kernels.cuh — sm_100a kernels of the explicit FE time step.
+//
+// One time step of /root/reference/Tools/Dynamic_solver.py:9-34 for one partition:
+//   F_int = LocalK.dot(d0)                         (:12, scipy csr_matvec order)
+//   F_ext = F_rankwise * linear_ramp(tn)           (:13, commons.py:7-11)
+//   d1    = (dt**2*(F_ext-F_int) + 2*M*d0 - M*dn + dt/2*M*alpha*dn) / (M + 0.5*alpha*M*dt)   (:17/:29)
+//   d1[Local_Dirichlet] = 0                        (:20/:32)
+// fused into a single pass over the matrix.  Arithmetic contract: every multiply, add, subtract and
+// divide below is an explicitly rounded binary64 intrinsic (__dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn),
+// which nvcc never contracts into FMA, and the row sum runs over the stored entries in order starting
+// from 0.0 — the same sequence of roundings scipy/numpy perform, hence bit-identical results.
+//
+// Storage (HBM): sliced ELL, slice height 32 = one warp.  Entry j of the row handled by lane l of slice
+// s lives at slice_ptr[s] + 32*j + l, so every warp-wide load of values (256 B) and column ids (128 B)
+// is one fully coalesced, 128-byte-aligned request.  Rows are ordered boundary-first (shared DOFs of the
+// partition interface, then interior) and, inside windows of SIGMA rows, by decreasing length, so
+// slices are almost padding-free; all vectors (d0, dn, M, F) live in that internal order and are
+// streamed coalesced.  The only non-streaming access is the gather d0[col].
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cg = cooperative_groups;
+
+struct SaaDev {
+    int64_t n_rows;            // padded rows (multiple of 32)
+    int64_t n_slices;          // n_rows / 32
+    int64_t sh_slices;         // slices [0, sh_slices) hold the shared (interface) DOFs
+    const int64_t *slice_ptr;  // [n_slices + 1] entry offsets, multiples of 32
+    const double *val;         // matrix values, sliced-ELL order
+    const int32_t *col;        // internal column ids, same order
+    const uint32_t *dir_mask;  // [n_slices] bit l set: row 32*s+l is a Dirichlet DOF
+    const double *M;           // lumped mass, internal order
+    const double *F;           // un-ramped load, internal order
+    double dt, dt2, dt_half, half_alpha, alpha;
+};
+
+// halo description on the device
+struct SaaHaloDev {
+    int64_t sh_rows;            // 32 * sh_slices
+    double *xbuf;               // [sh_rows own partial forces | received partial forces of all neighbours]
+    double *sendbuf;            // packed messages to all neighbours, concatenated
+    const int64_t *dst_ptr;     // [sh_rows + 1] CSR: where (in sendbuf) the partial force of a shared row goes
+    const int32_t *dst_pos;
+    const int64_t *src_ptr;     // [sh_rows + 1] CSR: sources (into xbuf) of a shared row, ASCENDING holder rank
+    const int32_t *src_pos;
+};
+
+__device__ __forceinline__ double ld_stream_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p)
+{
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// linear_ramp, commons.py:7-11
+__device__ __forceinline__ double saa_ramp(double t) { return (t <= 1.0) ? t : 1.0; }
+
+// Row sum of csr_matvec (Dynamic_solver.py:12): s = 0.0; s = s + (a_j * x[c_j]) in stored order.
+// Loads are issued UNROLL at a time ahead of the dependent add chain (memory-level parallelism);
+// the arithmetic order is untouched.
+//   NC_X: the gathered vector is constant for the whole launch (per-step kernels) -> read-only path;
+//         the persistent kernel re-reads vectors other blocks wrote before the last grid barrier and
+//         must use ordinary (coherent after the barrier's fence) loads.
+template <int UNROLL, bool NC_X>
+__device__ __forceinline__ double saa_row_dot(const SaaDev &P, int64_t slice, int lane, const double *x)
+{
+    const int64_t beg = P.slice_ptr[slice];
+    const int len = (int)((P.slice_ptr[slice + 1] - beg) >> 5);
+    const double *v = P.val + beg + lane;
+    const int32_t *c = P.col + beg + lane;
+    double s = 0.0;
+    int j = 0;
+    for (; j + UNROLL <= len; j += UNROLL) {
+        double a[UNROLL];
+        int32_t k[UNROLL];
+        double xv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            a[u] = ld_stream_f64(v + 32 * (j + u));
+            k[u] = ld_stream_s32(c + 32 * (j + u));
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) xv[u] = NC_X ? __ldg(x + k[u]) : x[k[u]];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) s = __dadd_rn(s, __dmul_rn(a[u], xv[u]));
+    }
+    for (; j < len; ++j) {
+        double a = ld_stream_f64(v + 32 * j);
+        int32_t k = ld_stream_s32(c + 32 * j);
+        s = __dadd_rn(s, __dmul_rn(a, NC_X ? __ldg(x + k) : x[k]));
+    }
+    return s;
+}
+
+// Dynamic_solver.py:17 / :29 with Python's left-to-right association (see oracle/fem_oracle.c)
+__device__ __forceinline__ double saa_cd_update(const SaaDev &P, double Fi, double F, double M, double d0, double dn,
+                                                double ramp)
+{
+    const double Fe = __dmul_rn(F, ramp);                                        // :13
+    const double t1 = __dmul_rn(P.dt2, __dsub_rn(Fe, Fi));                       // dt**2*(F_ext - F_int)
+    const double t2 = __dmul_rn(__dmul_rn(2.0, M), d0);                          // 2*l_M*d0
+    const double t3 = __dmul_rn(M, dn);                                          // l_M*dn
+    const double t4 = __dmul_rn(__dmul_rn(__dmul_rn(P.dt_half, M), P.alpha), dn);// dt/2*l_M*alpha*dn
+    const double num = __dadd_rn(__dsub_rn(__dadd_rn(t1, t2), t3), t4);
+    const double den = __dadd_rn(M, __dmul_rn(__dmul_rn(P.half_alpha, M), P.dt)); // l_M + 0.5*alpha*l_M*dt
+    return __ddiv_rn(num, den);
+}
+
+__device__ __forceinline__ void saa_finish_row(const SaaDev &P, int64_t slice, int lane, double Fi, const double *d0,
+                                               double *dn_d1, double ramp)
+{
+    const int64_t row = slice * 32 + lane;
+    const double d1 = saa_cd_update(P, Fi, P.F[row], P.M[row], d0[row], dn_d1[row], ramp);
+    const bool clamp = (P.dir_mask[slice] >> lane) & 1u;
+    dn_d1[row] = clamp ? 0.0 : d1;                                               // :20 / :32
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: fused force + update over slices [slice_begin, slice_end).  One warp per slice.
+//   ADD_ZERO: the synchronised path routes every force through f_global = 0; f_global += f
+//             (Distributed_tools.py:84-86), i.e. F_int = 0.0 + s; the local path uses s itself.
+// d1 overwrites dn in place (row i only needs its own dn[i]).  tn is read from device memory so that
+// the launch can be replayed from a CUDA graph; block 0 writes tn + dt for the next step (:235).
+template <bool ADD_ZERO>
+__global__ void __launch_bounds__(256) saa_k_step(SaaDev P, int64_t slice_begin, int64_t slice_end, const double *__restrict__ d0,
+                                                  double *__restrict__ dn_d1, const double *tn_in, double *tn_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = slice_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const double tn = *tn_in;
+    if (tn_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *tn_out = __dadd_rn(tn, P.dt);
+    if (slice >= slice_end) return;
+    double s = saa_row_dot<8, true>(P, slice, lane, d0);
+    if (ADD_ZERO) s = __dadd_rn(0.0, s);
+    saa_finish_row(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
+}
+
+// K2: partial internal force of the shared rows, stored for the own sum and packed into the messages
+// of every neighbour holding the node (fused halo pack).
+__global__ void __launch_bounds__(256) saa_k_boundary(SaaDev P, SaaHaloDev H, const double *__restrict__ d0)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slice >= P.sh_slices) return;
+    const double s = saa_row_dot<8, true>(P, slice, lane, d0);
+    const int64_t row = slice * 32 + lane;
+    H.xbuf[row] = s;
+    for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) H.sendbuf[H.dst_pos[k]] = s;
+}
+
+// K3: fused halo unpack + rank-ordered sum + update of the shared rows:
+//   F_int = ((0.0 + f_r0) + f_r1) + ...   holders r0 < r1 < ... (Distributed_tools.py:84-86)
+__global__ void __launch_bounds__(256) saa_k_shared_update(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
+                                                           double *__restrict__ dn_d1, const double *tn_in)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= H.sh_rows) return;
+    double Fi = 0.0;
+    for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) Fi = __dadd_rn(Fi, H.xbuf[H.src_pos[k]]);
+    saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(*tn_in));
+}
+
+// Persistent variant of K1 (local mode): one cooperative launch runs n_steps time steps; u stays in HBM/L2,
+// the two displacement buffers swap roles after each grid-wide barrier.  tn advances in registers with the
+// same sequence of additions as the host loop (Data_prepare.py:235).
+__global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, double *bufB, double *tn_io,
+                                                        int64_t n_steps)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    double tn = *tn_io;
+    double *d0 = bufA, *dn = bufB;
+    for (int64_t step = 0; step < n_steps; ++step) {
+        const double ramp = saa_ramp(tn);
+        for (int64_t slice = warp0; slice < P.n_slices; slice += nwarps) {
+            const double s = saa_row_dot<8, false>(P, slice, lane, d0);
+            saa_finish_row(P, slice, lane, s, d0, dn, ramp);
+        }
+        tn = __dadd_rn(tn, P.dt);
+        double *t = d0; d0 = dn; dn = t;
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *tn_io = tn;
+}
+
+// ---- small data-movement kernels -----------------------------------------------------------------------
+// external (reference local DOF order) <-> internal (boundary-first, sigma-sorted) order
+__global__ void saa_k_scatter_to_internal(int64_t n_ext, const int32_t *__restrict__ iperm, const double *__restrict__ src_ext,
+                                          double *__restrict__ dst_int)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ext) dst_int[iperm[i]] = src_ext[i];
+}
+__global__ void saa_k_gather_to_external(int64_t n_ext, const int32_t *__restrict__ iperm, const double *__restrict__ src_int,
+                                         double *__restrict__ dst_ext)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ext) dst_ext[i] = src_int[iperm[i]];
+}
+// history snapshot / prediction overwrite: rows[] are internal ids
+__global__ void saa_k_gather_rows(int64_t n, const int32_t *__restrict__ rows, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[rows[i]];
+}
+__global__ void saa_k_scatter_rows(int64_t n, const int32_t *__restrict__ rows, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[rows[i]] = src[i];
+}
