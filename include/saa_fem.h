@@ -98,6 +98,7 @@ int64_t saa_plan_n_dof(const saa_plan *plan);
 int64_t saa_plan_nnz(const saa_plan *plan);           /* stored entries of LocalK                         */
 int64_t saa_plan_padded_entries(const saa_plan *plan);/* entries streamed per step incl. slice padding    */
 int64_t saa_plan_kernel_launches(const saa_plan *plan);/* kernels launched by this plan so far            */
+int64_t saa_plan_matrix_bytes(const saa_plan *plan);  /* bytes of matrix storage streamed per step        */
 
 /* State = (d0, dn, tn) of Time_integration_displacement (commons.py:47-52), local DOF order. */
 int saa_plan_set_state(saa_plan *plan, const double *d0_host, const double *dn_host, double tn);
@@ -113,6 +114,8 @@ int saa_plan_get_state_dev(saa_plan *plan, double *d0_dev, double *dn_dev, doubl
  */
 int saa_plan_step(saa_plan *plan, int64_t n_steps, int mode, int launch);
 int saa_plan_synchronize(saa_plan *plan);
+/* the cudaStream_t the plan enqueues on (as void*), so that callers can record events on it */
+void *saa_plan_stream(saa_plan *plan);
 
 /*
  * The reference-facing call with HOST buffers: one evaluation of
@@ -132,6 +135,8 @@ int saa_plan_set_history(saa_plan *plan, const int64_t *dofs, int64_t n_dofs, in
 int64_t saa_plan_history_count(const saa_plan *plan);
 /* copy snapshots [first, first+count) (snapshot-major, n_dofs values each) to host memory */
 int saa_plan_read_history(saa_plan *plan, int64_t first, int64_t count, double *out_host);
+/* same, into device memory (asynchronous on the plan's stream) — feeds the on-device LSTM predictor */
+int saa_plan_read_history_dev(saa_plan *plan, int64_t first, int64_t count, double *out_dev);
 
 /*
  * Synchronization-avoiding mode (Online_predictor.py:280-301): `table` holds n_rows predictions of the

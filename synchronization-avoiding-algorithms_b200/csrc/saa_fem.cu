@@ -143,6 +143,9 @@ struct saa_group {
     cudaStream_t stream = nullptr;
 };
 
+// stream a plan's work is ordered on: its own, or its group's once it has joined one
+static inline cudaStream_t plan_stream(const saa_plan *p) { return p->group ? p->group->stream : p->stream; }
+
 extern "C" int saa_version(void) { return 100; }
 extern "C" const char *saa_last_error(void) { return g_err.c_str(); }
 extern "C" int saa_device_count(void)
@@ -411,6 +414,11 @@ extern "C" int64_t saa_plan_n_dof(const saa_plan *p) { return p ? p->n_dof : -1;
 extern "C" int64_t saa_plan_nnz(const saa_plan *p) { return p ? p->nnz : -1; }
 extern "C" int64_t saa_plan_padded_entries(const saa_plan *p) { return p ? p->padded_entries : -1; }
 extern "C" int64_t saa_plan_kernel_launches(const saa_plan *p) { return p ? p->launches : -1; }
+extern "C" int64_t saa_plan_matrix_bytes(const saa_plan *p)
+{
+    return p ? p->padded_entries * 12 + (p->n_slices + 1) * 8 + p->n_slices * 4 : -1;
+}
+extern "C" void *saa_plan_stream(saa_plan *p) { return p ? (void *)plan_stream(p) : nullptr; }
 
 static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -434,10 +442,10 @@ extern "C" int saa_plan_set_state(saa_plan *p, const double *d0, const double *d
     NEED_FINAL(p, "saa_plan_set_state");
     if (!d0 || !dn) return fail("saa_plan_set_state: null argument");
     CK(cudaSetDevice(p->device));
-    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    if (set_state_from_stage(p, p->stream, tn)) return -1;
-    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, plan_stream(p)));
+    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, plan_stream(p)));
+    if (set_state_from_stage(p, plan_stream(p), tn)) return -1;
+    CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
 
@@ -446,10 +454,10 @@ extern "C" int saa_plan_set_state_dev(saa_plan *p, const double *d0, const doubl
     NEED_FINAL(p, "saa_plan_set_state_dev");
     if (!d0 || !dn) return fail("saa_plan_set_state_dev: null argument");
     CK(cudaSetDevice(p->device));
-    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    if (set_state_from_stage(p, p->stream, tn)) return -1;
-    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, plan_stream(p)));
+    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, plan_stream(p)));
+    if (set_state_from_stage(p, plan_stream(p), tn)) return -1;
+    CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
 
@@ -465,11 +473,11 @@ extern "C" int saa_plan_get_state(saa_plan *p, double *d0, double *dn, double *t
 {
     NEED_FINAL(p, "saa_plan_get_state");
     CK(cudaSetDevice(p->device));
-    if (get_state_to_stage(p, p->stream, d0 != nullptr, dn != nullptr)) return -1;
-    if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
+    if (get_state_to_stage(p, plan_stream(p), d0 != nullptr, dn != nullptr)) return -1;
+    if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
+    if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
+    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
+    CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
 
@@ -477,11 +485,11 @@ extern "C" int saa_plan_get_state_dev(saa_plan *p, double *d0, double *dn, doubl
 {
     NEED_FINAL(p, "saa_plan_get_state_dev");
     CK(cudaSetDevice(p->device));
-    if (get_state_to_stage(p, p->stream, d0 != nullptr, dn != nullptr)) return -1;
-    if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
+    if (get_state_to_stage(p, plan_stream(p), d0 != nullptr, dn != nullptr)) return -1;
+    if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, plan_stream(p)));
+    if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, plan_stream(p)));
+    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
+    CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
 
@@ -514,10 +522,27 @@ extern "C" int saa_plan_read_history(saa_plan *p, int64_t first, int64_t count, 
     if (first < 0 || count < 0 || first + count > p->hist_count) return fail("saa_plan_read_history: range out of bounds");
     if (first < p->hist_count - p->hist_cap) return fail("saa_plan_read_history: snapshots already overwritten");
     CK(cudaSetDevice(p->device));
-    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaStreamSynchronize(plan_stream(p)));
     for (int64_t s = 0; s < count; ++s) {
         const int64_t slot = (first + s) % p->hist_cap;
         CK(cudaMemcpy(out + s * p->hist_n, p->d_hist + slot * p->hist_n, p->hist_n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int saa_plan_read_history_dev(saa_plan *p, int64_t first, int64_t count, double *out)
+{
+    NEED_FINAL(p, "saa_plan_read_history_dev");
+    if (first < 0 || count < 0 || first + count > p->hist_count) return fail("saa_plan_read_history_dev: range out of bounds");
+    if (first < p->hist_count - p->hist_cap) return fail("saa_plan_read_history_dev: snapshots already overwritten");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = plan_stream(p);
+    for (int64_t s = 0; s < count;) {       // contiguous runs of the ring
+        const int64_t slot = (first + s) % p->hist_cap;
+        const int64_t run = std::min(count - s, p->hist_cap - slot);
+        CK(cudaMemcpyAsync(out + s * p->hist_n, p->d_hist + slot * p->hist_n, run * p->hist_n * sizeof(double),
+                           cudaMemcpyDeviceToDevice, st));
+        s += run;
     }
     return 0;
 }

@@ -100,7 +100,7 @@ __device__ __forceinline__ double saa_row_dot(const SaaDev &P, int64_t slice, in
     return s;
 }
 
-// Dynamic_solver.py:17 / :29 with Python's left-to-right association (see oracle/fem_oracle.c)
+// Dynamic_solver.py:17 / :29 with Python's left-to-right association
 __device__ __forceinline__ double saa_cd_update(const SaaDev &P, double Fi, double F, double M, double d0, double dn,
                                                 double ramp)
 {

@@ -1,0 +1,309 @@
+"""ctypes binding of the C ABI in include/saa_fem.h (csrc/libsaa_fem.so) — the device plan of one partition.
+
+`StepPlan` owns what one MPI rank of the reference hands to
+`parallel_explicit_solver_dis_pre` every step (/root/reference/Tools/Dynamic_solver.py:9-10):
+LocalK, F_rankwise, l_M, Local_Dirichlet, dt, alpha — uploaded once — plus the state
+(d0, dn, tn) of `Time_integration_displacement` (Tools/commons.py:47-52), resident in HBM.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible, every
+constructor / compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_CSRC, "libsaa_fem.so")
+_lib = None
+
+MODE_LOCAL, MODE_SYNC, MODE_PREDICT = 0, 1, 2
+LAUNCH_AUTO, LAUNCH_PER_STEP, LAUNCH_GRAPH, LAUNCH_PERSISTENT = 0, 1, 2, 3
+
+# every symbol include/saa_fem.h declares: name -> (restype, argtypes)
+_vp, _i64, _i32, _f64, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_int
+_PP = ctypes.POINTER(ctypes.c_void_p)
+ABI = {
+    "saa_version": (_int, []),
+    "saa_last_error": (ctypes.c_char_p, []),
+    "saa_device_count": (_int, []),
+    "saa_plan_create": (_int, [_PP, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64]),
+    "saa_plan_set_halo": (_int, [_vp, _int, _int, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "saa_plan_finalize": (_int, [_vp]),
+    "saa_plan_destroy": (_int, [_vp]),
+    "saa_plan_n_dof": (_i64, [_vp]),
+    "saa_plan_nnz": (_i64, [_vp]),
+    "saa_plan_padded_entries": (_i64, [_vp]),
+    "saa_plan_kernel_launches": (_i64, [_vp]),
+    "saa_plan_matrix_bytes": (_i64, [_vp]),
+    "saa_plan_set_state": (_int, [_vp, _vp, _vp, _f64]),
+    "saa_plan_get_state": (_int, [_vp, _vp, _vp, _vp]),
+    "saa_plan_set_state_dev": (_int, [_vp, _vp, _vp, _f64]),
+    "saa_plan_get_state_dev": (_int, [_vp, _vp, _vp, _vp]),
+    "saa_plan_step": (_int, [_vp, _i64, _int, _int]),
+    "saa_plan_synchronize": (_int, [_vp]),
+    "saa_plan_stream": (_vp, [_vp]),
+    "saa_step_host": (_int, [_vp, _vp, _vp, _f64, _int, _vp]),
+    "saa_plan_set_history": (_int, [_vp, _vp, _i64, _i64, _i64]),
+    "saa_plan_history_count": (_i64, [_vp]),
+    "saa_plan_read_history": (_int, [_vp, _i64, _i64, _vp]),
+    "saa_plan_read_history_dev": (_int, [_vp, _i64, _i64, _vp]),
+    "saa_plan_set_prediction": (_int, [_vp, _vp, _i64, _vp, _i64]),
+    "saa_group_create": (_int, [_PP, _PP, _int]),
+    "saa_group_step": (_int, [_vp, _i64, _int, _int]),
+    "saa_group_synchronize": (_int, [_vp]),
+    "saa_group_destroy": (_int, [_vp]),
+    "saa_nccl_unique_id": (_int, [_vp]),
+    "saa_plan_init_nccl": (_int, [_vp, _vp]),
+}
+
+
+class SaaError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _SO
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/libsaa_fem.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "saa_fem.h"))
+    stale = (not os.path.isfile(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        r = subprocess.run(["make", "-C", _CSRC] + (["-B"] if force else []), capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(r.stdout, r.stderr)
+        if r.returncode:
+            raise SaaError("building libsaa_fem.so failed")
+    return _SO
+
+
+def lib():
+    """Load libsaa_fem.so and declare every prototype of include/saa_fem.h.  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(_SO):
+            raise SaaError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the time-step path)")
+        L = ctypes.CDLL(_SO, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in ABI.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc, what=""):
+    if rc != 0:
+        raise SaaError(f"{what}: {lib().saa_last_error().decode(errors='replace')}")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def step_scalars(dt, alpha):
+    """Scalar sub-expressions of Dynamic_solver.py:17 with the reference's own Python expressions on the
+    reference's own types (dt: np.float64, so `dt**2` is numpy's power; alpha: Python float)."""
+    dt = np.float64(dt)
+    return float(dt), float(dt ** 2), float(dt / 2), float(0.5 * alpha), float(alpha)
+
+
+class StepPlan:
+    """Device-resident problem + state of one partition (one reference MPI rank)."""
+
+    def __init__(self, LocalK, F_rankwise, l_M, Local_Dirichlet, dt, alpha, device=0, halo=None, rank=0, size=1):
+        """LocalK: scipy CSR (sorted indices; its stored order is the summation order).
+        halo: dict from maps.halo_plan(rank, size, rank_nodal_list) when size > 1."""
+        L = lib()
+        K = LocalK.tocsr() if not hasattr(LocalK, "indptr") else LocalK
+        n = K.shape[0]
+        if int(K.indptr[-1]) >= 2 ** 31:
+            raise SaaError("LocalK has more than 2^31 stored entries; use the 64-bit device assembly path")
+        self._indptr = np.ascontiguousarray(K.indptr, dtype=np.int32)
+        self._indices = np.ascontiguousarray(K.indices, dtype=np.int32)
+        self._data = np.ascontiguousarray(K.data, dtype=np.float64)
+        F = np.ascontiguousarray(F_rankwise, dtype=np.float64).reshape(-1)
+        M = np.ascontiguousarray(l_M, dtype=np.float64).reshape(-1)
+        D = np.ascontiguousarray(Local_Dirichlet, dtype=np.int64).reshape(-1)
+        if F.size != n or M.size != n:
+            raise SaaError(f"F_rankwise/l_M have {F.size}/{M.size} entries, LocalK has {n} rows")
+        self.n_dof, self.rank, self.size, self.device = n, int(rank), int(size), int(device)
+        self.dt, self.dt2, self.dt_half, self.half_alpha, self.alpha = step_scalars(dt, alpha)
+        h = ctypes.c_void_p()
+        _check(L.saa_plan_create(ctypes.byref(h), device, n, _p(self._indptr), _p(self._indices), _p(self._data),
+                                 _p(F), _p(M), _p(D), D.size, self.dt, self.dt2, self.dt_half, self.half_alpha,
+                                 self.alpha), "saa_plan_create")
+        self.h = h
+        if size > 1:
+            if halo is None:
+                raise SaaError("size > 1 needs the halo description (maps.halo_plan)")
+            nb = np.ascontiguousarray(halo["neighbours"], dtype=np.int32)
+            ptr = np.zeros(nb.size + 1, dtype=np.int64)
+            for k, r in enumerate(halo["neighbours"]):
+                ptr[k + 1] = ptr[k] + halo["send_idx"][r].size
+            send = (np.concatenate([halo["send_idx"][r] for r in halo["neighbours"]]) if nb.size
+                    else np.zeros(0, dtype=np.int64)).astype(np.int64)
+            sp = np.ascontiguousarray(halo["shared_pos"], dtype=np.int64)
+            hp = np.ascontiguousarray(halo["holders_ptr"], dtype=np.int64)
+            hr = np.ascontiguousarray(halo["holders_rank"], dtype=np.int32)
+            hs = np.ascontiguousarray(halo["holders_slot"], dtype=np.int64)
+            _check(L.saa_plan_set_halo(h, rank, size, sp.size, _p(sp), nb.size, _p(nb), _p(ptr), _p(send), _p(hp),
+                                       _p(hr), _p(hs)), "saa_plan_set_halo")
+        _check(L.saa_plan_finalize(h), "saa_plan_finalize")
+        del self._indptr, self._indices, self._data
+
+    # ---- facts -------------------------------------------------------------------------------------
+    @property
+    def nnz(self):
+        return int(lib().saa_plan_nnz(self.h))
+
+    @property
+    def padded_entries(self):
+        return int(lib().saa_plan_padded_entries(self.h))
+
+    @property
+    def matrix_bytes(self):
+        """bytes of matrix storage the step kernel streams per time step"""
+        return int(lib().saa_plan_matrix_bytes(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(lib().saa_plan_kernel_launches(self.h))
+
+    @property
+    def stream(self):
+        """raw cudaStream_t of the plan (int) — wrap with torch.cuda.ExternalStream to time on it"""
+        return int(lib().saa_plan_stream(self.h) or 0)
+
+    # ---- state -------------------------------------------------------------------------------------
+    def set_state(self, d0, dn, tn):
+        d0 = np.ascontiguousarray(d0, dtype=np.float64).reshape(-1)
+        dn = np.ascontiguousarray(dn, dtype=np.float64).reshape(-1)
+        if d0.size != self.n_dof or dn.size != self.n_dof:
+            raise SaaError("set_state: wrong vector length")
+        _check(lib().saa_plan_set_state(self.h, _p(d0), _p(dn), float(tn)), "saa_plan_set_state")
+
+    def get_state(self):
+        d0, dn = np.empty(self.n_dof), np.empty(self.n_dof)
+        tn = ctypes.c_double(0)
+        _check(lib().saa_plan_get_state(self.h, _p(d0), _p(dn), ctypes.byref(tn)), "saa_plan_get_state")
+        return d0, dn, tn.value
+
+    def d0(self):
+        d0 = np.empty(self.n_dof)
+        _check(lib().saa_plan_get_state(self.h, _p(d0), None, None), "saa_plan_get_state")
+        return d0
+
+    def set_state_dev(self, d0_ptr, dn_ptr, tn):
+        _check(lib().saa_plan_set_state_dev(self.h, d0_ptr, dn_ptr, float(tn)), "saa_plan_set_state_dev")
+
+    def get_state_dev(self, d0_ptr, dn_ptr):
+        tn = ctypes.c_double(0)
+        _check(lib().saa_plan_get_state_dev(self.h, d0_ptr, dn_ptr, ctypes.byref(tn)), "saa_plan_get_state_dev")
+        return tn.value
+
+    # ---- stepping ----------------------------------------------------------------------------------
+    def step(self, n_steps=1, mode=MODE_LOCAL, launch=LAUNCH_AUTO):
+        _check(lib().saa_plan_step(self.h, int(n_steps), int(mode), int(launch)), "saa_plan_step")
+
+    def synchronize(self):
+        _check(lib().saa_plan_synchronize(self.h), "saa_plan_synchronize")
+
+    def step_host(self, d0, dn, tn, mode=MODE_LOCAL, out=None):
+        """One parallel_explicit_solver_dis_pre evaluation with host buffers -> d1 (n_dof,)."""
+        d0 = np.ascontiguousarray(d0, dtype=np.float64).reshape(-1)
+        dn = np.ascontiguousarray(dn, dtype=np.float64).reshape(-1)
+        if d0.size != self.n_dof or dn.size != self.n_dof:
+            raise SaaError("step_host: wrong vector length")
+        d1 = np.empty(self.n_dof) if out is None else out
+        _check(lib().saa_step_host(self.h, _p(d0), _p(dn), float(tn), int(mode), _p(d1)), "saa_step_host")
+        return d1
+
+    # ---- history / prediction ----------------------------------------------------------------------
+    def set_history(self, dofs, capacity, save_every=1):
+        d = None if dofs is None else np.ascontiguousarray(dofs, dtype=np.int64).reshape(-1)
+        self._hist_n = self.n_dof if d is None else d.size
+        _check(lib().saa_plan_set_history(self.h, _p(d), self._hist_n, int(capacity), int(save_every)),
+               "saa_plan_set_history")
+
+    @property
+    def history_count(self):
+        return int(lib().saa_plan_history_count(self.h))
+
+    def read_history(self, first=0, count=None):
+        count = self.history_count - first if count is None else count
+        out = np.empty((count, self._hist_n))
+        _check(lib().saa_plan_read_history(self.h, int(first), int(count), _p(out)), "saa_plan_read_history")
+        return out
+
+    def read_history_dev(self, first, count, dev_ptr):
+        _check(lib().saa_plan_read_history_dev(self.h, int(first), int(count), dev_ptr), "saa_plan_read_history_dev")
+
+    def set_prediction(self, dofs, table_dev_ptr, n_rows):
+        d = None if dofs is None else np.ascontiguousarray(dofs, dtype=np.int64).reshape(-1)
+        n = self._pred_n if d is None else d.size
+        self._pred_n = n
+        _check(lib().saa_plan_set_prediction(self.h, _p(d), n, table_dev_ptr, int(n_rows)), "saa_plan_set_prediction")
+
+    # ---- NCCL transport ----------------------------------------------------------------------------
+    def init_nccl(self, unique_id: bytes):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().saa_plan_init_nccl(self.h, buf), "saa_plan_init_nccl")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().saa_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().saa_nccl_unique_id(buf), "saa_nccl_unique_id")
+    return buf.raw
+
+
+class PlanGroup:
+    """All P partitions in ONE process on one GPU, stepped together; the halo exchange is a set of
+    device-to-device copies.  Used to run a P-way partition when fewer than P GPUs are available
+    (and by the parity tests, which need every P on a single B200)."""
+
+    def __init__(self, plans):
+        self.plans = list(plans)
+        arr = (ctypes.c_void_p * len(self.plans))(*[p.h for p in self.plans])
+        h = ctypes.c_void_p()
+        _check(lib().saa_group_create(ctypes.byref(h), arr, len(self.plans)), "saa_group_create")
+        self.h = h
+
+    def step(self, n_steps=1, mode=MODE_SYNC, launch=LAUNCH_AUTO):
+        _check(lib().saa_group_step(self.h, int(n_steps), int(mode), int(launch)), "saa_group_step")
+
+    def synchronize(self):
+        _check(lib().saa_group_synchronize(self.h), "saa_group_synchronize")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().saa_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count():
+    return int(lib().saa_device_count())

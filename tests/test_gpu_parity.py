@@ -1,0 +1,235 @@
+"""Parity of the CUDA time-step path (through the C ABI of include/saa_fem.h) with the reference.
+
+Bit-exact (fp64 compared as uint64) against
+  * the golden histories produced by the unmodified reference (tests/golden, oracle/gen_golden.py),
+  * the CPU oracle (oracle/fem_oracle.c) on seeded random states and on larger meshes,
+for P = 1 (serial short-circuit, Dynamic_solver.py:25) and P > 1 (syn_cpus semantics,
+Distributed_tools.py:77-92) with all partitions of a run resident on the one GPU of the test box.
+The north-star tolerance is rel-L2 <= 1e-12 on displacement histories; bit-equality implies it.
+"""
+import numpy as np
+import pytest
+
+import saa_b200  # noqa: F401
+from saa_b200 import maps, mesh, partition, plan as splan, problem
+from util import bits_equal, golden_names, load_golden, make_oracle, oracle_module
+
+pytestmark = pytest.mark.gpu
+
+
+def golden_plans(g):
+    P = g["P"]
+    lists = [r["nodes"] for r in g["ranks"]]
+    plans = []
+    for q, r in enumerate(g["ranks"]):
+        import scipy.sparse as sp
+        n = r["F"].size
+        K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+        halo = maps.halo_plan(q, P, lists) if P > 1 else None
+        plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), halo=halo,
+                                    rank=q, size=P))
+    grp = splan.PlanGroup(plans) if P > 1 else None
+    return plans, grp
+
+
+def run(plans, grp, n, mode):
+    if grp is None:
+        plans[0].step(n, splan.MODE_LOCAL if mode != splan.MODE_PREDICT else mode)
+        plans[0].synchronize()
+    else:
+        grp.step(n, mode)
+        grp.synchronize()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_histories_equal_reference_bitwise(name):
+    g = load_golden(name)
+    plans, grp = golden_plans(g)
+    done = 0
+    for n in [int(s) for s in g["steps"]]:
+        run(plans, grp, n - done, splan.MODE_SYNC)
+        done = n
+        for q in range(g["P"]):
+            d0, dn, tn = plans[q].get_state()
+            assert bits_equal(d0, g[f"hist_{n}_r{q}"]), (name, n, q)
+    # tn accumulated by repeated addition (Data_prepare.py:235)
+    t = 0
+    for _ in range(done):
+        t = t + float(g["dt"])
+    assert tn == t
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if len(load_golden(n)["nosync_steps"])])
+def test_cuda_unsynchronised_branch_equals_reference_bitwise(name):
+    """MODEL=True (Dynamic_solver.py:22): every partition steps on its own, no exchange."""
+    g = load_golden(name)
+    plans, grp = golden_plans(g)
+    done = 0
+    for n in [int(s) for s in g["nosync_steps"]]:
+        run(plans, grp, n - done, splan.MODE_LOCAL)
+        done = n
+        for q in range(g["P"]):
+            assert bits_equal(plans[q].d0(), g[f"nosync_{n}_r{q}"]), (name, n, q)
+
+
+def test_relative_l2_tolerance_statement():
+    """The north-star criterion spelled out: rel-L2 <= 1e-12 on the displacement history of config 1
+    (beam_coarse, np=2) — here it is exactly 0."""
+    g = load_golden("beam_coarse_P2")
+    plans, grp = golden_plans(g)
+    done = 0
+    for n in [int(s) for s in g["steps"]]:
+        run(plans, grp, n - done, splan.MODE_SYNC)
+        done = n
+        for q in range(2):
+            ref = g[f"hist_{n}_r{q}"]
+            err = np.linalg.norm(plans[q].d0() - ref) / max(np.linalg.norm(ref), 1e-300)
+            assert err <= 1e-12
+
+
+@pytest.mark.parametrize("launch", [splan.LAUNCH_PER_STEP, splan.LAUNCH_GRAPH, splan.LAUNCH_PERSISTENT])
+@pytest.mark.parametrize("nsteps", [1, 2, 7, 100, 1001])
+def test_launch_strategies_are_bit_identical(launch, nsteps):
+    g = load_golden("struct_m3_P1")
+    plans, _ = golden_plans(g)
+    o = make_oracle(g)
+    # non-trivial start: 300 oracle steps
+    o.run(300)
+    d0, dn, tn = o.state(0)
+    plans[0].set_state(d0, dn, tn)
+    plans[0].step(nsteps, splan.MODE_LOCAL, launch)
+    plans[0].synchronize()
+    o.run(nsteps)
+    e0, en, etn = o.state(0)
+    c0, cn, ctn = plans[0].get_state()
+    assert bits_equal(c0, e0) and bits_equal(cn, en) and ctn == etn
+
+
+@pytest.mark.parametrize("name", ["beam_coarse_P1", "beam_coarse_P4", "struct_m2_P2"])
+def test_step_host_is_one_reference_call(name):
+    """saa_step_host == one parallel_explicit_solver_dis_pre evaluation on caller-provided (d0, dn, tn)
+    (local / MODEL=True arithmetic), random finite states incl. tn > 1 (ramp saturated, commons.py:7-11)."""
+    g = load_golden(name)
+    plans = [golden_plans_single(g, q) for q in range(g["P"])]
+    fo = oracle_module()
+    rng = np.random.default_rng(7)
+    for q, pl in enumerate(plans):
+        r = g["ranks"][q]
+        n = r["F"].size
+        for tn in (0.0, 0.37, 1.0, 1.7):
+            d0 = rng.standard_normal(n) * 1e-3
+            dn = rng.standard_normal(n) * 1e-3
+            o = fo.OracleProblem(len(g["points"]), [r], g["dt"], float(g["alpha"]))
+            o.set_state(0, d0, dn, tn)
+            o.run(1, model=True)
+            got = pl.step_host(d0, dn, tn, splan.MODE_LOCAL)
+            assert bits_equal(got, o.d0(0)), (name, q, tn)
+            o.close()
+
+
+def golden_plans_single(g, q):
+    import scipy.sparse as sp
+    r = g["ranks"][q]
+    n = r["F"].size
+    K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+    return splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]))
+
+
+def test_history_ring_and_save_every():
+    """d1_save of Data_prepare.py:219,238-240: column j is the d1 of loop index j*save_every."""
+    g = load_golden("beam_coarse_P1")
+    plans, _ = golden_plans(g)
+    pl = plans[0]
+    dofs = np.array([5, 17, 100, 329, 0])
+    pl.set_history(dofs, capacity=64, save_every=3)
+    pl.step(100, splan.MODE_LOCAL)
+    pl.synchronize()
+    assert pl.history_count == 34                         # i = 0, 3, ..., 99
+    H = pl.read_history()
+    o = make_oracle(g)
+    for j in range(34):
+        o.run(3 * j + 1 - (3 * (j - 1) + 1 if j else 0))
+        assert bits_equal(H[j], o.d0(0)[dofs]), j
+    # ring: only the last `capacity` snapshots stay readable
+    pl.set_history(None, capacity=4, save_every=1)
+    pl.step(10, splan.MODE_LOCAL)
+    pl.synchronize()
+    assert pl.history_count == 10
+    with pytest.raises(splan.SaaError):
+        pl.read_history(0, 10)
+    last = pl.read_history(6, 4)
+    assert bits_equal(last[-1], pl.d0())
+
+
+def test_prediction_mode_overwrites_shared_dofs():
+    """Online_predictor.py:294-301: un-synchronised step, then d1[loc_dof_shared] = table row."""
+    import torch
+    g = load_golden("beam_coarse_P2")
+    q = 1
+    pl = golden_plans_single(g, q)
+    r = g["ranks"][q]
+    dofs = r["loc_dof_shared"]
+    rng = np.random.default_rng(11)
+    table = rng.standard_normal((6, dofs.size)) * 1e-4
+    tdev = torch.from_numpy(table).cuda()
+    pl.set_prediction(dofs, tdev.data_ptr(), 6)
+    pl.step(6, splan.MODE_PREDICT)
+    pl.synchronize()
+    fo = oracle_module()
+    o = fo.OracleProblem(len(g["points"]), [r], g["dt"], float(g["alpha"]))
+    for k in range(6):
+        o.run(1, model=True)
+        d0, dn, tn = o.state(0)
+        d0[dofs] = table[k]
+        o.set_state(0, d0, dn, tn)
+    assert bits_equal(pl.d0(), o.d0(0))
+    with pytest.raises(splan.SaaError):
+        pl.step(1, splan.MODE_PREDICT)                     # table exhausted
+
+
+@pytest.mark.parametrize("m,P,part", [(5, 1, "metis"), (5, 4, "metis"), (6, 8, "metis"), (6, 3, "slab")])
+def test_sparse_setup_plus_cuda_equals_oracle_on_larger_meshes(m, P, part):
+    """Meshes beyond what the reference's dense set-up is practical for: product set-up (sparse assembly,
+    METIS / slab partition, vectorised maps) -> CUDA group vs the CPU oracle on the same inputs, bitwise."""
+    pts, cells, fac = mesh.structured_beam(m)
+    ep = partition.metis_part_mesh(cells, len(pts), P) if part == "metis" else partition.slab_partition(pts, cells, P)
+    pb = problem.build_problem(pts, cells, fac, ep, P)
+    plans, grp = problem.make_group(pb)
+    fo = oracle_module()
+    ranks = [dict(K_indptr=pb["ranks"][r]["K"].indptr, K_indices=pb["ranks"][r]["K"].indices,
+                  K_data=pb["ranks"][r]["K"].data, F=pb["ranks"][r]["F"], lM=pb["ranks"][r]["lM"],
+                  dirichlet=pb["ranks"][r]["dirichlet"], nodes=pb["ranks"][r]["nodes"]) for r in range(P)]
+    o = fo.OracleProblem(len(pts), ranks, pb["dt"], problem.DAMP_DEFAULT)
+    for n in (1, 50, 250):
+        run(plans, grp, n, splan.MODE_SYNC)
+        o.run(n)
+        for r in range(P):
+            assert bits_equal(plans[r].d0(), o.d0(r)), (m, P, n, r)
+    # synchronised partitions agree on every shared node (each holds the same summed force)
+    if P > 1:
+        glob = {}
+        for r in range(P):
+            d = plans[r].d0().reshape(-1, 3)
+            for k in pb["ranks"][r]["halo"]["shared_pos"]:
+                gid = int(pb["ranks"][r]["nodes"][k])
+                if gid in glob:
+                    assert bits_equal(glob[gid], d[k])
+                glob[gid] = d[k].copy()
+
+
+def test_errors_are_reported():
+    g = load_golden("beam_coarse_P1")
+    pl = golden_plans_single(g, 0)
+    with pytest.raises(splan.SaaError):
+        pl.set_state(np.zeros(3), np.zeros(3), 0.0)
+    with pytest.raises(splan.SaaError):
+        pl.step(-1)
+    g2 = load_golden("beam_coarse_P2")
+    lists = [r["nodes"] for r in g2["ranks"]]
+    import scipy.sparse as sp
+    r = g2["ranks"][0]
+    n = r["F"].size
+    K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+    p0 = splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g2["dt"], 0.5, halo=maps.halo_plan(0, 2, lists), rank=0, size=2)
+    with pytest.raises(splan.SaaError):
+        p0.step(1, splan.MODE_SYNC)                        # no transport attached
