@@ -147,6 +147,22 @@ int saa_plan_read_history_dev(saa_plan *plan, int64_t first, int64_t count, doub
 int saa_plan_set_prediction(saa_plan *plan, const int64_t *dofs, int64_t n_dofs, const double *table_dev,
                             int64_t n_rows);
 
+/* ---- caller-provided transport: the neighbour messages pass through HOST memory, so any communicator the
+ * caller already has (mpi4py as in the reference, gloo, ...) can carry them.  Layout of the send / receive
+ * buffers: neighbour k (ascending rank nb_rank[k]) owns doubles [msg_off[k], msg_off[k+1]); both sides of an
+ * interface list the common nodes in ascending global node id, 3 doubles (x, y, z) per node. ----------- */
+int saa_plan_halo_layout(const saa_plan *plan, int *n_nb, int32_t *nb_rank, int64_t *msg_off, int capacity);
+/* One synchronised step in two halves (Dynamic_solver.py:12 ... syn_cpus ... :29-32):
+ *   begin: partial forces of the shared rows -> send_host (returns when the messages are in host memory;
+ *          the interior rows keep running on the GPU while the caller exchanges)
+ *   end:   recv_host (the neighbours' send buffers, same layout) -> rank-ordered sum, update, rotation   */
+int saa_plan_step_begin_host(saa_plan *plan, double *send_host);
+int saa_plan_step_end_host(saa_plan *plan, const double *recv_host);
+/* syn_cpus (Distributed_tools.py:77-92) on a caller-provided force vector f (host, local DOF order):
+ *   begin: pack the shared entries of f into send_host;  end: out = f_global[dofs_local]               */
+int saa_plan_forces_begin_host(saa_plan *plan, const double *f_host, double *send_host);
+int saa_plan_forces_end_host(saa_plan *plan, const double *recv_host, double *out_host);
+
 /* ---- several partitions in one process (P ranks on fewer GPUs; exchange by device copies) ---------- */
 int saa_group_create(saa_group **out, saa_plan **plans, int n_plans);
 int saa_group_step(saa_group *grp, int64_t n_steps, int mode, int launch);

@@ -1,0 +1,49 @@
+"""The explicit time step behind the reference's signature (/root/reference/Tools/Dynamic_solver.py:9-34)."""
+import weakref
+
+import numpy as np
+
+from saa_b200 import maps as _maps
+from saa_b200 import plan as _plan
+from Tools.Mat_construction import *   # noqa: F401,F403  (same re-export chain as the reference, :2-5)
+from Tools.commons import *            # noqa: F401,F403
+from Tools.Distributed_tools import *  # noqa: F401,F403
+import Tools.Distributed_tools as _dt
+
+_plans = {}
+
+
+def _plan_for(LocalK, F_rankwise, Local_nodes, Local_Dirichlet, T, l_M, alpha, size, rank):
+    """One device plan per LocalK object: built (and, for size > 1, given its interface description — a
+    collective) at the first call, reused afterwards."""
+    key = id(LocalK)
+    hit = _plans.get(key)
+    if hit is not None and hit[0]() is LocalK and hit[2] == (float(T.dt), float(alpha), size, rank):
+        return hit[1]
+    halo = None
+    if size != 1:
+        nodes = np.asarray(Local_nodes, dtype=np.int64)
+        c = _dt.comm
+        lists = c.allgather(nodes) if hasattr(c, "allgather") else c.bcast(c.gather(nodes, root=0), root=0)
+        halo = _maps.halo_plan(rank, size, lists)
+    p = _plan.StepPlan(LocalK, F_rankwise, l_M, Local_Dirichlet, T.dt, alpha, halo=halo, rank=rank, size=size)
+    _plans[key] = (weakref.ref(LocalK), p, (float(T.dt), float(alpha), size, rank))
+    return p
+
+
+def parallel_explicit_solver_dis_pre(LocalK, F_rankwise, Points, Local_nodes, Local_Dirichlet,
+                                     T, Elas, l_M, alpha, size, rank, MODEL=False):
+    """d_{n+1} from T = (tn, dt, d0 = d_n, dn = d_{n-1}); returns a fresh writable (3n,1) float64 array.
+
+    MODEL == False and size != 1: collective — the partial internal forces of shared nodes are summed over
+    their holders in ascending rank order (syn_cpus semantics) before the update.  MODEL == True: local.
+    T.d0 / T.dn are not modified.
+    """
+    p = _plan_for(LocalK, F_rankwise, Local_nodes, Local_Dirichlet, T, l_M, alpha, size, rank)
+    if MODEL or size == 1:
+        d1 = p.step_host(T.d0, T.dn, T.tn, _plan.MODE_LOCAL)
+    else:
+        p.set_state(T.d0, T.dn, T.tn)
+        p.step_exchange(_dt.comm.exchange)
+        d1 = p.d0()
+    return d1.reshape(-1, 1)

@@ -283,3 +283,33 @@ def lumped_mass_and_load(points, cells, rho, fz, exact_rowsum=None):
         lM[prow[rstart]] = Mrow
         l_M = np.repeat(lM, 3).reshape(3 * N, 1)
     return l_M, F.reshape(3 * N, 1)
+
+
+def consistent_mass_csr(points, cells, rho):
+    """Consistent mass matrix of the whole mesh as CSR (the M of Global_Assembly*, Mat_construction.py:62,68,
+    199-231): scalar node-pair values Me[a,b] = sum_q N_a rho N_b detJ w on the three diagonal components,
+    element contributions added in ascending element order."""
+    cells = np.asarray(cells, dtype=np.int64)
+    N = points.shape[0]
+    P = points[cells[:, :4]]
+    detJ = np.linalg.det(_jacobians(P))
+    xi = _N_QUAD_POINTS
+    shp = np.stack([1. - xi[:, 0] - xi[:, 1] - xi[:, 2], xi[:, 0], xi[:, 1], xi[:, 2]], axis=1)
+    Me = np.zeros((cells.shape[0], 4, 4))
+    for q in range(4):
+        for i in range(4):
+            for j in range(4):
+                Me[:, i, j] = Me[:, i, j] + shp[q, i] * rho * shp[q, j] * detJ * _W_QUAD[q]
+    rn = np.repeat(cells[:, :, None], 4, axis=2).reshape(-1)
+    cn = np.repeat(cells[:, None, :], 4, axis=1).reshape(-1)
+    key = rn * np.int64(N) + cn
+    perm = np.argsort(key, kind="stable")
+    ks = key[perm]
+    start = np.empty(ks.size, dtype=bool)
+    start[0] = True
+    start[1:] = ks[1:] != ks[:-1]
+    Mpair = _grouped_sequential_sum(start, Me.reshape(-1)[perm])
+    prow, pcol = ks[start] // N, ks[start] % N
+    rows = (3 * prow[:, None] + np.arange(3)[None, :]).ravel()
+    cols = (3 * pcol[:, None] + np.arange(3)[None, :]).ravel()
+    return csr_matrix((np.repeat(Mpair, 3), (rows, cols)), shape=(3 * N, 3 * N))

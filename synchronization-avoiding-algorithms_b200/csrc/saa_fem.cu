@@ -136,6 +136,9 @@ struct saa_plan {
     int64_t launches = 0;
     saa_ncclComm_t comm = nullptr;
     saa_group *group = nullptr;
+    cudaEvent_t ev_msg = nullptr;
+    bool in_split_step = false;             // between saa_plan_step_begin_host and saa_plan_step_end_host
+    double *d_force = nullptr;              // [2 * n_rows] scratch of the stand-alone force synchronisation
 };
 
 struct saa_group {
@@ -400,10 +403,11 @@ extern "C" int saa_plan_destroy(saa_plan *p)
             if (p->graph_exec[i]) cudaGraphExecDestroy(p->graph_exec[i]);
         void *ptrs[] = {p->d_slice_ptr, p->d_val, p->d_col, p->d_M, p->d_F, p->d_dir, p->d_iperm, p->d_buf[0], p->d_buf[1],
                         p->d_tn, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
-                        p->d_hist_rows, p->d_hist, p->d_pred_rows};
+                        p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force};
         for (void *q : ptrs)
             if (q) cudaFree(q);
         if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+        if (p->ev_msg) cudaEventDestroy(p->ev_msg);
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;
@@ -731,6 +735,95 @@ extern "C" int saa_step_host(saa_plan *p, const double *d0, const double *dn, do
     if (saa_plan_step(p, 1, mode, SAA_LAUNCH_PER_STEP)) return -1;
     if (get_state_to_stage(p, st, true, false)) return -1;
     CK(cudaMemcpyAsync(d1, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- caller-provided transport (MPI through mpi4py, gloo, ...): the messages pass through host memory ----
+extern "C" int saa_plan_halo_layout(const saa_plan *p, int *n_nb, int32_t *nb_rank, int64_t *msg_off, int cap)
+{
+    if (!p || !p->finalized) return fail("saa_plan_halo_layout: plan not finalized");
+    const int n = (int)p->nb_rank.size();
+    if (n_nb) *n_nb = n;
+    if (nb_rank && msg_off) {
+        if (cap < n) return fail("saa_plan_halo_layout: capacity %d < %d neighbours", cap, n);
+        for (int k = 0; k < n; ++k) nb_rank[k] = p->nb_rank[k];
+        for (int k = 0; k <= n; ++k) msg_off[k] = p->msg_off.empty() ? 0 : p->msg_off[k];
+    }
+    return 0;
+}
+
+extern "C" int saa_plan_step_begin_host(saa_plan *p, double *send_host)
+{
+    NEED_FINAL(p, "saa_plan_step_begin_host");
+    if (p->group) return fail("saa_plan_step_begin_host: plan belongs to a group");
+    CK(cudaSetDevice(p->device));
+    sync_phase_boundary(p, p->stream);
+    if (p->total_msg > 0) {
+        if (!send_host) return fail("saa_plan_step_begin_host: null send buffer");
+        CK(cudaMemcpyAsync(send_host, p->d_send, p->total_msg * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (!p->ev_msg) CK(cudaEventCreateWithFlags(&p->ev_msg, cudaEventDisableTiming));
+        CK(cudaEventRecord(p->ev_msg, p->stream));
+    }
+    // interior rows do not depend on the exchange: enqueue them now so that they overlap the caller's transport
+    sync_phase_interior(p, p->stream);
+    CK(cudaGetLastError());
+    if (p->total_msg > 0) CK(cudaEventSynchronize(p->ev_msg));   // wait for the messages only, not for the interior rows
+    p->in_split_step = true;
+    return 0;
+}
+
+extern "C" int saa_plan_step_end_host(saa_plan *p, const double *recv_host)
+{
+    NEED_FINAL(p, "saa_plan_step_end_host");
+    if (!p->in_split_step) return fail("saa_plan_step_end_host without saa_plan_step_begin_host");
+    CK(cudaSetDevice(p->device));
+    if (p->total_msg > 0) {
+        if (!recv_host) return fail("saa_plan_step_end_host: null receive buffer");
+        CK(cudaMemcpyAsync(p->d_xbuf + p->H.sh_rows, recv_host, p->total_msg * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    sync_phase_shared(p, p->stream);
+    p->in_split_step = false;
+    if (after_step(p, p->stream, SAA_MODE_SYNC)) return -1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// syn_cpus on a caller-provided force vector (external local DOF order, host memory)
+extern "C" int saa_plan_forces_begin_host(saa_plan *p, const double *f_host, double *send_host)
+{
+    NEED_FINAL(p, "saa_plan_forces_begin_host");
+    if (!f_host) return fail("saa_plan_forces_begin_host: null argument");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = plan_stream(p);
+    if (!p->d_force) CK(cudaMalloc((void **)&p->d_force, 2 * p->n_rows * sizeof(double)));
+    CK(cudaMemsetAsync(p->d_force, 0, p->n_rows * sizeof(double), st));
+    CK(cudaMemcpyAsync(p->d_stage, f_host, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
+    saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage, p->d_force);
+    p->launches++;
+    if (p->sh_slices > 0) {
+        saa_k_pack_forces<<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->H, p->d_force);
+        p->launches++;
+        if (p->total_msg > 0 && send_host)
+            CK(cudaMemcpyAsync(send_host, p->d_send, p->total_msg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int saa_plan_forces_end_host(saa_plan *p, const double *recv_host, double *out_host)
+{
+    NEED_FINAL(p, "saa_plan_forces_end_host");
+    if (!out_host || !p->d_force) return fail("saa_plan_forces_end_host: null argument or no begin call");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = plan_stream(p);
+    if (p->total_msg > 0 && recv_host)
+        CK(cudaMemcpyAsync(p->d_xbuf + p->H.sh_rows, recv_host, p->total_msg * sizeof(double), cudaMemcpyHostToDevice, st));
+    double *sum = p->d_force + p->n_rows;
+    saa_k_sum_forces<<<nblk(p->n_rows, 256), 256, 0, st>>>(p->n_rows, p->H, p->d_force, sum);
+    saa_k_gather_to_external<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, sum, p->d_stage);
+    p->launches += 2;
+    CK(cudaMemcpyAsync(out_host, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -168,6 +168,30 @@ __global__ void __launch_bounds__(256) saa_k_shared_update(SaaDev P, SaaHaloDev 
     saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(*tn_in));
 }
 
+// syn_cpus as a stand-alone operation (Distributed_tools.py:77-92) on a caller-provided force vector:
+// pack the shared rows of f (internal order) into the neighbour messages ...
+__global__ void saa_k_pack_forces(SaaHaloDev H, const double *__restrict__ f)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= H.sh_rows) return;
+    const double s = f[row];
+    H.xbuf[row] = s;
+    for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) H.sendbuf[H.dst_pos[k]] = s;
+}
+// ... and, after the exchange, f_global[dofs_local]: rank-ordered sum on shared rows, 0.0 + f elsewhere (:84-86)
+__global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__restrict__ f, double *__restrict__ out)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double Fi = 0.0;
+    if (row < H.sh_rows) {
+        for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) Fi = __dadd_rn(Fi, H.xbuf[H.src_pos[k]]);
+    } else {
+        Fi = __dadd_rn(Fi, f[row]);
+    }
+    out[row] = Fi;
+}
+
 // Persistent variant of K1 (local mode): one cooperative launch runs n_steps time steps; u stays in HBM/L2,
 // the two displacement buffers swap roles after each grid-wide barrier.  tn advances in registers with the
 // same sequence of additions as the host loop (Data_prepare.py:235).

@@ -53,6 +53,11 @@ ABI = {
     "saa_plan_read_history": (_int, [_vp, _i64, _i64, _vp]),
     "saa_plan_read_history_dev": (_int, [_vp, _i64, _i64, _vp]),
     "saa_plan_set_prediction": (_int, [_vp, _vp, _i64, _vp, _i64]),
+    "saa_plan_halo_layout": (_int, [_vp, _vp, _vp, _vp, _int]),
+    "saa_plan_step_begin_host": (_int, [_vp, _vp]),
+    "saa_plan_step_end_host": (_int, [_vp, _vp]),
+    "saa_plan_forces_begin_host": (_int, [_vp, _vp, _vp]),
+    "saa_plan_forces_end_host": (_int, [_vp, _vp, _vp]),
     "saa_group_create": (_int, [_PP, _PP, _int]),
     "saa_group_step": (_int, [_vp, _i64, _int, _int]),
     "saa_group_synchronize": (_int, [_vp]),
@@ -251,6 +256,40 @@ class StepPlan:
         n = self._pred_n if d is None else d.size
         self._pred_n = n
         _check(lib().saa_plan_set_prediction(self.h, _p(d), n, table_dev_ptr, int(n_rows)), "saa_plan_set_prediction")
+
+    # ---- caller-provided transport (messages through host memory) -----------------------------------
+    def halo_layout(self):
+        """(neighbour ranks ascending, message offsets in doubles) of the send / receive buffers."""
+        n = ctypes.c_int(0)
+        _check(lib().saa_plan_halo_layout(self.h, ctypes.byref(n), None, None, 0), "saa_plan_halo_layout")
+        nb = np.zeros(n.value, dtype=np.int32)
+        off = np.zeros(n.value + 1, dtype=np.int64)
+        _check(lib().saa_plan_halo_layout(self.h, ctypes.byref(n), _p(nb), _p(off), n.value), "saa_plan_halo_layout")
+        return nb, off
+
+    def step_exchange(self, exchange):
+        """One synchronised step with the caller's transport: `exchange(send, nb, off) -> recv` moves
+        send[off[k]:off[k+1]] to rank nb[k] and returns the buffer received from the neighbours (same layout)."""
+        if not hasattr(self, "_nb"):
+            self._nb, self._off = self.halo_layout()
+            self._send = np.zeros(max(int(self._off[-1]), 1))
+        _check(lib().saa_plan_step_begin_host(self.h, _p(self._send)), "saa_plan_step_begin_host")
+        recv = np.ascontiguousarray(exchange(self._send[:int(self._off[-1])], self._nb, self._off), dtype=np.float64)
+        _check(lib().saa_plan_step_end_host(self.h, _p(recv)), "saa_plan_step_end_host")
+
+    def sync_forces(self, f, exchange):
+        """syn_cpus on a host force vector: returns f_global[dofs_local] (n_dof,)."""
+        if not hasattr(self, "_nb"):
+            self._nb, self._off = self.halo_layout()
+            self._send = np.zeros(max(int(self._off[-1]), 1))
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        if f.size != self.n_dof:
+            raise SaaError("sync_forces: wrong vector length")
+        _check(lib().saa_plan_forces_begin_host(self.h, _p(f), _p(self._send)), "saa_plan_forces_begin_host")
+        recv = np.ascontiguousarray(exchange(self._send[:int(self._off[-1])], self._nb, self._off), dtype=np.float64)
+        out = np.empty(self.n_dof)
+        _check(lib().saa_plan_forces_end_host(self.h, _p(recv), _p(out)), "saa_plan_forces_end_host")
+        return out
 
     # ---- NCCL transport ----------------------------------------------------------------------------
     def init_nccl(self, unique_id: bytes):
