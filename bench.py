@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--launch", default="auto", choices=["auto", "per_step", "graph", "persistent"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo transport for N > 1")
     return ap.parse_args()
 
 
@@ -191,7 +192,7 @@ def main():
     import torch
     import torch.distributed as dist
     import saa_b200  # noqa: F401
-    from saa_b200 import plan as splan, problem
+    from saa_b200 import multi, plan as splan, problem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,10 +211,7 @@ def main():
     pb, part, n_nodes, n_el = build_rank_problem(m, world, rank)
     q = pb["ranks"][rank]
     pl = problem.make_plan(q, pb["dt"], problem.DAMP_DEFAULT, world, device=local)
-    if world > 1:
-        ids = [splan.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        pl.init_nccl(ids[0])
+    transport = multi.attach_transport(pl, args.transport) if world > 1 else "none"
     t_setup = time.time() - t_setup
     n_dof_global = 3 * n_nodes
     n_dof_local = pl.n_dof
@@ -297,7 +295,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"structured 25x1x1 cantilever (Mesh_info/beam_US.geo box) m={m}: {n_dof_global} DOF, "
                                    f"{n_el} tets; BASELINE config 2 (~1M DOF, fp64)",
-                       "partition": part, "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
+                       "partition": part, "transport": transport, "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
                        "launch": args.launch, "dt": dtv, "setup_s": round(t_setup, 1),
                        "l2": "inputs larger than L2: matrix stream per step = %.0f MB vs 126 MB L2" % (pl.matrix_bytes / 1e6)},
             "e2e": {"value": n_dof_global * args.e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",

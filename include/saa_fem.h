@@ -169,6 +169,21 @@ int saa_group_step(saa_group *grp, int64_t n_steps, int mode, int launch);
 int saa_group_synchronize(saa_group *grp);
 int saa_group_destroy(saa_group *grp);
 
+/* ---- one partition per process / GPU of one node: halo exchange by peer-memory stores over NVLink -----------
+ * Every rank exports the CUDA IPC handle of its receive area (saa_plan_peer_export), the handles are
+ * distributed by the caller (torch.distributed / MPI), and saa_plan_peer_attach maps the neighbours' areas:
+ *   handles64     n_nb x 64 bytes, neighbour k = nb_rank[k] of saa_plan_halo_layout
+ *   remote_off    offset (doubles) of THIS rank's message inside neighbour k's receive area (its msg_off)
+ *   remote_total  neighbour k's total message length (its msg_off[n_nb]) — the parity stride of its area
+ *   remote_slot   index of THIS rank in neighbour k's neighbour list (selects its arrival flag)
+ *   remote_n_nb   neighbour k's number of neighbours
+ * Afterwards SAA_MODE_SYNC steps run as three stream-ordered kernels per step (pack + peer store + flag,
+ * interior rows, wait + rank-ordered sum + update) with no host or NCCL call, replayed from a CUDA graph.
+ * All ranks must execute the same number of synchronised steps.                                           */
+int saa_plan_peer_export(saa_plan *plan, void *handle64, int64_t *total_msg);
+int saa_plan_peer_attach(saa_plan *plan, int n_nb, const void *handles64, const int64_t *remote_off,
+                         const int64_t *remote_total, const int32_t *remote_slot, const int32_t *remote_n_nb);
+
 /* ---- one partition per process / GPU: halo exchange over NCCL (NVLink) -------------------------------- */
 /* 128-byte NCCL unique id, created on one rank and distributed by the caller (torch.distributed) */
 int saa_nccl_unique_id(void *id128);

@@ -112,13 +112,26 @@ struct saa_plan {
     int32_t *d_col = nullptr, *d_iperm = nullptr;
     uint32_t *d_dir = nullptr;
     double *d_buf[2] = {nullptr, nullptr};  // displacement levels; d0 = d_buf[cur], dn = d_buf[cur^1]
-    double *d_tn = nullptr;                 // [2], tn = d_tn[cur]
+    SaaClock *d_clk = nullptr;              // [2], (tn, sync_step) = d_clk[cur]
     int cur = 0;
     double *d_stage = nullptr;              // 3*n_dof staging in external order (state I/O)
     // halo device
     double *d_xbuf = nullptr, *d_send = nullptr;
+    double *d_recv = nullptr;               // peer region: [2 parities x total_msg doubles | n_nb arrival flags (u64)]
+    unsigned int *d_done = nullptr;
+    int32_t *d_dst_nb = nullptr;
+    // peer-memory transport
+    bool peer = false;
+    SaaHaloDev Hp{};                        // H with the peer destination table
+    int32_t *d_dst_pos_peer = nullptr;
+    double **d_peer_recv = nullptr;
+    int64_t *d_peer_stride = nullptr;
+    unsigned long long **d_peer_flag = nullptr;
+    std::vector<void *> peer_mapped;        // cudaIpcOpenMemHandle results (closed on destroy)
+    cudaGraphExec_t graph_peer[2] = {nullptr, nullptr};
     int64_t *d_dst_ptr = nullptr, *d_src_ptr = nullptr;
     int32_t *d_dst_pos = nullptr, *d_src_pos = nullptr;
+    std::vector<int32_t> dst_pos_h, dst_nb_h; // host copies of the pack table (rebased by saa_plan_peer_attach)
     std::vector<int64_t> msg_off;           // [n_nb+1] offsets (in doubles) of each neighbour's message
     int64_t total_msg = 0;
     // history ring
@@ -323,8 +336,8 @@ extern "C" int saa_plan_finalize(saa_plan *p)
         CK(cudaMalloc((void **)&p->d_buf[b], p->n_rows * sizeof(double)));
         CK(cudaMemset(p->d_buf[b], 0, p->n_rows * sizeof(double)));
     }
-    CK(cudaMalloc((void **)&p->d_tn, 2 * sizeof(double)));
-    CK(cudaMemset(p->d_tn, 0, 2 * sizeof(double)));
+    CK(cudaMalloc((void **)&p->d_clk, 2 * sizeof(SaaClock)));
+    CK(cudaMemset(p->d_clk, 0, 2 * sizeof(SaaClock)));
     CK(cudaMalloc((void **)&p->d_stage, 3 * n * sizeof(double)));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
 
@@ -339,14 +352,16 @@ extern "C" int saa_plan_finalize(saa_plan *p)
         p->msg_off.assign(n_nb + 1, 0);
         for (int k = 0; k < n_nb; ++k) p->msg_off[k + 1] = p->msg_off[k] + 3 * (p->nb_ptr[k + 1] - p->nb_ptr[k]);
         p->total_msg = p->msg_off[n_nb];
-        if (sh_pad + p->total_msg >= (int64_t)INT32_MAX) return fail("halo too large");
+        if (sh_pad + 2 * p->total_msg >= (int64_t)INT32_MAX) return fail("halo too large");
         // internal row of (shared node j, component c)
         auto irow = [&](int64_t j, int c) { return (int64_t)p->iperm_h[3 * p->shared_pos[j] + c]; };
-        std::vector<std::vector<int32_t>> dst(sh_pad), src(sh_pad);
+        std::vector<std::vector<int32_t>> dst(sh_pad), dstk(sh_pad), src(sh_pad);
         for (int k = 0; k < n_nb; ++k)
             for (int64_t e = p->nb_ptr[k]; e < p->nb_ptr[k + 1]; ++e)
-                for (int c = 0; c < 3; ++c)
+                for (int c = 0; c < 3; ++c) {
                     dst[irow(p->send_idx[e], c)].push_back((int32_t)(p->msg_off[k] + 3 * (e - p->nb_ptr[k]) + c));
+                    dstk[irow(p->send_idx[e], c)].push_back((int32_t)k);
+                }
         for (int64_t j = 0; j < n_shared; ++j)
             for (int64_t h = p->holders_ptr[j]; h < p->holders_ptr[j + 1]; ++h) {
                 if (h > p->holders_ptr[j] && p->holders_rank[h] <= p->holders_rank[h - 1])
@@ -363,21 +378,33 @@ extern "C" int saa_plan_finalize(saa_plan *p)
                 }
             }
         std::vector<int64_t> dst_ptr(sh_pad + 1, 0), src_ptr(sh_pad + 1, 0);
-        std::vector<int32_t> dst_pos, src_pos;
+        std::vector<int32_t> dst_pos, dst_nb, src_pos;
         for (int64_t r = 0; r < sh_pad; ++r) {
             dst_pos.insert(dst_pos.end(), dst[r].begin(), dst[r].end());
+            dst_nb.insert(dst_nb.end(), dstk[r].begin(), dstk[r].end());
             src_pos.insert(src_pos.end(), src[r].begin(), src[r].end());
             dst_ptr[r + 1] = (int64_t)dst_pos.size();
             src_ptr[r + 1] = (int64_t)src_pos.size();
         }
+        p->dst_pos_h = dst_pos; p->dst_nb_h = dst_nb;
         if (upload(&p->d_dst_ptr, dst_ptr) || upload(&p->d_dst_pos, dst_pos) || upload(&p->d_src_ptr, src_ptr) ||
             upload(&p->d_src_pos, src_pos))
             return -1;
-        CK(cudaMalloc((void **)&p->d_xbuf, (sh_pad + p->total_msg) * sizeof(double)));
-        CK(cudaMemset(p->d_xbuf, 0, (sh_pad + p->total_msg) * sizeof(double)));
+        CK(cudaMalloc((void **)&p->d_xbuf, sh_pad * sizeof(double)));
+        CK(cudaMemset(p->d_xbuf, 0, sh_pad * sizeof(double)));
+        const size_t region = (size_t)(2 * p->total_msg) * sizeof(double) + (size_t)std::max(n_nb, 1) * sizeof(unsigned long long);
+        CK(cudaMalloc((void **)&p->d_recv, region));
+        CK(cudaMemset(p->d_recv, 0, region));
+        CK(cudaMalloc((void **)&p->d_done, sizeof(unsigned int)));
+        CK(cudaMemset(p->d_done, 0, sizeof(unsigned int)));
+        if (upload(&p->d_dst_nb, dst_nb)) return -1;
         CK(cudaMalloc((void **)&p->d_send, std::max<int64_t>(p->total_msg, 1) * sizeof(double)));
         p->H.sh_rows = sh_pad; p->H.xbuf = p->d_xbuf; p->H.sendbuf = p->d_send;
-        p->H.dst_ptr = p->d_dst_ptr; p->H.dst_pos = p->d_dst_pos; p->H.src_ptr = p->d_src_ptr; p->H.src_pos = p->d_src_pos;
+        p->H.recv = p->d_recv; p->H.recv_stride = p->total_msg;
+        p->H.dst_ptr = p->d_dst_ptr; p->H.dst_pos = p->d_dst_pos; p->H.dst_nb = p->d_dst_nb;
+        p->H.src_ptr = p->d_src_ptr; p->H.src_pos = p->d_src_pos;
+        p->H.n_nb = n_nb; p->H.done_ctr = p->d_done;
+        p->H.flags = (const unsigned long long *)(p->d_recv + 2 * p->total_msg);
     }
 
     // cooperative launch geometry for the persistent kernel
@@ -399,10 +426,14 @@ extern "C" int saa_plan_destroy(saa_plan *p)
     if (p->finalized) {
         cudaSetDevice(p->device);
         if (p->stream) cudaStreamSynchronize(p->stream);
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i) {
             if (p->graph_exec[i]) cudaGraphExecDestroy(p->graph_exec[i]);
+            if (p->graph_peer[i]) cudaGraphExecDestroy(p->graph_peer[i]);
+        }
+        for (void *m : p->peer_mapped) cudaIpcCloseMemHandle(m);
         void *ptrs[] = {p->d_slice_ptr, p->d_val, p->d_col, p->d_M, p->d_F, p->d_dir, p->d_iperm, p->d_buf[0], p->d_buf[1],
-                        p->d_tn, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
+                        p->d_clk, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
+                        p->d_recv, p->d_done, p->d_dst_nb, p->d_dst_pos_peer, p->d_peer_recv, p->d_peer_stride, p->d_peer_flag,
                         p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force};
         for (void *q : ptrs)
             if (q) cudaFree(q);
@@ -436,7 +467,7 @@ static int set_state_from_stage(saa_plan *p, cudaStream_t st, double tn)
     saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage, p->d_buf[p->cur]);
     saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage + p->n_dof, p->d_buf[p->cur ^ 1]);
     p->launches += 2;
-    CK(cudaMemcpyAsync(p->d_tn + p->cur, &tn, sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(&p->d_clk[p->cur].tn, &tn, sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaGetLastError());
     return 0;
 }
@@ -480,7 +511,7 @@ extern "C" int saa_plan_get_state(saa_plan *p, double *d0, double *dn, double *t
     if (get_state_to_stage(p, plan_stream(p), d0 != nullptr, dn != nullptr)) return -1;
     if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
     if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
-    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
+    if (tn) CK(cudaMemcpyAsync(tn, &p->d_clk[p->cur].tn, sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
     CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
@@ -492,7 +523,7 @@ extern "C" int saa_plan_get_state_dev(saa_plan *p, double *d0, double *dn, doubl
     if (get_state_to_stage(p, plan_stream(p), d0 != nullptr, dn != nullptr)) return -1;
     if (d0) CK(cudaMemcpyAsync(d0, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, plan_stream(p)));
     if (dn) CK(cudaMemcpyAsync(dn, p->d_stage + p->n_dof, p->n_dof * sizeof(double), cudaMemcpyDeviceToDevice, plan_stream(p)));
-    if (tn) CK(cudaMemcpyAsync(tn, p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
+    if (tn) CK(cudaMemcpyAsync(tn, &p->d_clk[p->cur].tn, sizeof(double), cudaMemcpyDeviceToHost, plan_stream(p)));
     CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
@@ -593,7 +624,7 @@ static int after_step(saa_plan *p, cudaStream_t st, int mode)
 static void launch_local_step(saa_plan *p, cudaStream_t st)
 {
     saa_k_step<false><<<nblk(p->n_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
-        p->D, 0, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_tn + p->cur, p->d_tn + (p->cur ^ 1));
+        p->D, 0, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1));
     p->cur ^= 1;
     p->launches++;
 }
@@ -608,7 +639,8 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
     if (hooks && launch != SAA_LAUNCH_PER_STEP) return fail("history / prediction hooks need SAA_LAUNCH_PER_STEP");
     if (launch == SAA_LAUNCH_PERSISTENT) {
         if (p->coop_blocks <= 0) return fail("cooperative launch not available");
-        double *a = p->d_buf[p->cur], *b = p->d_buf[p->cur ^ 1], *tn = p->d_tn + p->cur;
+        double *a = p->d_buf[p->cur], *b = p->d_buf[p->cur ^ 1];
+        SaaClock *tn = p->d_clk + p->cur;
         int64_t ns = n_steps;
         void *args[] = {&p->D, &a, &b, &tn, &ns};
         int64_t want = (p->n_slices + SAA_WARPS_PER_BLOCK - 1) / SAA_WARPS_PER_BLOCK;
@@ -616,7 +648,7 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
         CK(cudaLaunchCooperativeKernel((void *)saa_k_persistent, dim3(blocks), dim3(32 * SAA_WARPS_PER_BLOCK), args, 0, st));
         p->launches++;
         if (n_steps & 1) {   // an odd number of steps swaps the buffer roles; tn was written back to d_tn[cur]
-            CK(cudaMemcpyAsync(p->d_tn + (p->cur ^ 1), p->d_tn + p->cur, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(p->d_clk + (p->cur ^ 1), p->d_clk + p->cur, sizeof(SaaClock), cudaMemcpyDeviceToDevice, st));
             p->cur ^= 1;
         }
         p->step_index += n_steps;
@@ -654,7 +686,10 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
 static void sync_phase_boundary(saa_plan *p, cudaStream_t st)
 {
     if (p->sh_slices > 0) {
-        saa_k_boundary<<<nblk(p->sh_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(p->D, p->H, p->d_buf[p->cur]);
+        if (p->peer)
+            saa_k_boundary<true><<<nblk(p->sh_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(p->D, p->Hp, p->d_buf[p->cur], p->d_clk + p->cur);
+        else
+            saa_k_boundary<false><<<nblk(p->sh_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(p->D, p->H, p->d_buf[p->cur], p->d_clk + p->cur);
         p->launches++;
     }
 }
@@ -663,13 +698,16 @@ static void sync_phase_interior(saa_plan *p, cudaStream_t st)
     // also advances tn; runs even with zero interior slices so that tn moves
     const int64_t n_in = p->n_slices - p->sh_slices;
     saa_k_step<true><<<std::max(1u, nblk(n_in, SAA_WARPS_PER_BLOCK)), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
-        p->D, p->sh_slices, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_tn + p->cur, p->d_tn + (p->cur ^ 1));
+        p->D, p->sh_slices, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1));
     p->launches++;
 }
 static void sync_phase_shared(saa_plan *p, cudaStream_t st)
 {
     if (p->sh_slices > 0) {
-        saa_k_shared_update<<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_tn + p->cur);
+        if (p->peer)
+            saa_k_shared_update<true><<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur);
+        else
+            saa_k_shared_update<false><<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur);
         p->launches++;
     }
     p->cur ^= 1;
@@ -686,12 +724,53 @@ static int step_sync_nccl(saa_plan *p, int64_t n_steps)
             for (int k = 0; k < n_nb; ++k) {
                 const size_t cnt = (size_t)(p->msg_off[k + 1] - p->msg_off[k]);
                 NCK(g_nccl.Send(p->d_send + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
-                NCK(g_nccl.Recv(p->d_xbuf + p->H.sh_rows + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
+                NCK(g_nccl.Recv(p->d_recv + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
             }
             NCK(g_nccl.GroupEnd());
         }
         sync_phase_interior(p, st);
         sync_phase_shared(p, st);
+        if (after_step(p, st, SAA_MODE_SYNC)) return -1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// peer transport: three stream-ordered kernels per step, no host involvement -> replayed from a two-step graph
+static void launch_peer_step(saa_plan *p, cudaStream_t st)
+{
+    sync_phase_boundary(p, st);
+    sync_phase_interior(p, st);
+    sync_phase_shared(p, st);
+}
+
+static int step_sync_peer(saa_plan *p, int64_t n_steps, int launch)
+{
+    cudaStream_t st = p->stream;
+    const bool hooks = p->hist_cap > 0;
+    int64_t done = 0;
+    if (!hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) {
+        const int c = p->cur;
+        if (!p->graph_peer[c]) {
+            cudaGraph_t g;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int64_t l0 = p->launches;
+            launch_peer_step(p, st);
+            launch_peer_step(p, st);
+            p->launches = l0;
+            CK(cudaStreamEndCapture(st, &g));
+            CK(cudaGraphInstantiate(&p->graph_peer[c], g, 0));
+            CK(cudaGraphDestroy(g));
+        }
+        const int per = (p->sh_slices > 0 ? 3 : 1) * 2;
+        for (; done + 2 <= n_steps; done += 2) {
+            CK(cudaGraphLaunch(p->graph_peer[c], st));
+            p->launches += per;
+        }
+        p->step_index += done;
+    }
+    for (; done < n_steps; ++done) {
+        launch_peer_step(p, st);
         if (after_step(p, st, SAA_MODE_SYNC)) return -1;
     }
     CK(cudaGetLastError());
@@ -708,7 +787,8 @@ extern "C" int saa_plan_step(saa_plan *p, int64_t n_steps, int mode, int launch)
     if (mode == SAA_MODE_SYNC) {
         if (p->size == 1) return step_local(p, n_steps, SAA_MODE_LOCAL, launch);   // Dynamic_solver.py:25 `if size != 1`
         if (p->group) return fail("saa_plan_step: this plan belongs to a group; use saa_group_step");
-        if (!p->comm) return fail("saa_plan_step: SAA_MODE_SYNC needs a transport (saa_plan_init_nccl or saa_group_create)");
+        if (p->peer) return step_sync_peer(p, n_steps, launch);
+        if (!p->comm) return fail("saa_plan_step: SAA_MODE_SYNC needs a transport (saa_plan_peer_attach, saa_plan_init_nccl or saa_group_create)");
         return step_sync_nccl(p, n_steps);
     }
     return fail("saa_plan_step: unknown mode %d", mode);
@@ -780,7 +860,7 @@ extern "C" int saa_plan_step_end_host(saa_plan *p, const double *recv_host)
     CK(cudaSetDevice(p->device));
     if (p->total_msg > 0) {
         if (!recv_host) return fail("saa_plan_step_end_host: null receive buffer");
-        CK(cudaMemcpyAsync(p->d_xbuf + p->H.sh_rows, recv_host, p->total_msg * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaMemcpyAsync(p->d_recv, recv_host, p->total_msg * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     }
     sync_phase_shared(p, p->stream);
     p->in_split_step = false;
@@ -818,7 +898,7 @@ extern "C" int saa_plan_forces_end_host(saa_plan *p, const double *recv_host, do
     CK(cudaSetDevice(p->device));
     cudaStream_t st = plan_stream(p);
     if (p->total_msg > 0 && recv_host)
-        CK(cudaMemcpyAsync(p->d_xbuf + p->H.sh_rows, recv_host, p->total_msg * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(p->d_recv, recv_host, p->total_msg * sizeof(double), cudaMemcpyHostToDevice, st));
     double *sum = p->d_force + p->n_rows;
     saa_k_sum_forces<<<nblk(p->n_rows, 256), 256, 0, st>>>(p->n_rows, p->H, p->d_force, sum);
     saa_k_gather_to_external<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, sum, p->d_stage);
@@ -875,7 +955,7 @@ extern "C" int saa_group_step(saa_group *g, int64_t n_steps, int mode, int launc
                     saa_plan *b = g->plans[a->nb_rank[k]];
                     size_t kk = std::find(b->nb_rank.begin(), b->nb_rank.end(), (int32_t)i) - b->nb_rank.begin();
                     // a receives from b the message b packed for a
-                    CK(cudaMemcpyAsync(a->d_xbuf + a->H.sh_rows + a->msg_off[k], b->d_send + b->msg_off[kk],
+                    CK(cudaMemcpyAsync(a->d_recv + a->msg_off[k], b->d_send + b->msg_off[kk],
                                        (a->msg_off[k + 1] - a->msg_off[k]) * sizeof(double), cudaMemcpyDeviceToDevice, st));
                 }
             }
@@ -911,6 +991,61 @@ extern "C" int saa_group_destroy(saa_group *g)
     for (saa_plan *p : g->plans) p->group = nullptr;
     cudaStreamDestroy(g->stream);
     delete g;
+    return 0;
+}
+
+// ---- peer-memory transport over NVLink: one process per GPU of one node ------------------------------------
+extern "C" int saa_plan_peer_export(saa_plan *p, void *handle64, int64_t *total_msg)
+{
+    NEED_FINAL(p, "saa_plan_peer_export");
+    if (!handle64) return fail("saa_plan_peer_export: null argument");
+    if (!p->d_recv) return fail("saa_plan_peer_export: this plan has no interface");
+    CK(cudaSetDevice(p->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p->d_recv));
+    memcpy(handle64, &h, sizeof h);
+    if (total_msg) *total_msg = p->total_msg;
+    return 0;
+}
+
+extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64, const int64_t *remote_off,
+                                    const int64_t *remote_total, const int32_t *remote_slot, const int32_t *remote_n_nb)
+{
+    NEED_FINAL(p, "saa_plan_peer_attach");
+    if (n_nb != (int)p->nb_rank.size()) return fail("saa_plan_peer_attach: %d handles for %d neighbours", n_nb, (int)p->nb_rank.size());
+    if (p->peer) return fail("saa_plan_peer_attach: already attached");
+    if (n_nb > 256) return fail("saa_plan_peer_attach: more than 256 neighbours");
+    if (n_nb == 0) { p->peer = true; p->Hp = p->H; return 0; }
+    if (!handles64 || !remote_off || !remote_total || !remote_slot || !remote_n_nb) return fail("saa_plan_peer_attach: null argument");
+    CK(cudaSetDevice(p->device));
+    std::vector<double *> recv(n_nb);
+    std::vector<unsigned long long *> flag(n_nb);
+    std::vector<int64_t> stride(n_nb);
+    for (int k = 0; k < n_nb; ++k) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles64 + 64 * k, sizeof h);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_mapped.push_back(ptr);
+        if (remote_slot[k] < 0 || remote_slot[k] >= remote_n_nb[k]) return fail("saa_plan_peer_attach: bad remote slot");
+        recv[k] = (double *)ptr;
+        stride[k] = remote_total[k];
+        flag[k] = (unsigned long long *)((double *)ptr + 2 * remote_total[k]) + remote_slot[k];
+    }
+    // destination table inside the neighbours' receive areas: same entries as the pack table, rebased
+    std::vector<int32_t> pos(p->dst_pos_h.size());
+    for (size_t i = 0; i < pos.size(); ++i) {
+        const int k = p->dst_nb_h[i];
+        pos[i] = (int32_t)(p->dst_pos_h[i] - p->msg_off[k] + remote_off[k]);
+        if (pos[i] < 0 || pos[i] >= remote_total[k]) return fail("saa_plan_peer_attach: destination outside the neighbour's receive area");
+    }
+    if (upload(&p->d_dst_pos_peer, pos) || upload(&p->d_peer_recv, recv) || upload(&p->d_peer_stride, stride) || upload(&p->d_peer_flag, flag))
+        return -1;
+    p->Hp = p->H;
+    p->Hp.dst_pos = p->d_dst_pos_peer;
+    p->Hp.peer_recv = p->d_peer_recv; p->Hp.peer_stride = p->d_peer_stride; p->Hp.peer_flag = p->d_peer_flag;
+    p->peer = true;
     return 0;
 }
 

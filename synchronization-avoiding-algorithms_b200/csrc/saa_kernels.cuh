@@ -36,16 +36,44 @@ struct SaaDev {
     double dt, dt2, dt_half, half_alpha, alpha;
 };
 
+// (tn, number of synchronised steps so far) live in device memory so that launches can be replayed from a
+// CUDA graph; every step reads slot `cur` and writes slot `cur ^ 1`.
+struct SaaClock {
+    double tn;
+    unsigned long long sync_step;
+};
+
 // halo description on the device
 struct SaaHaloDev {
     int64_t sh_rows;            // 32 * sh_slices
-    double *xbuf;               // [sh_rows own partial forces | received partial forces of all neighbours]
-    double *sendbuf;            // packed messages to all neighbours, concatenated
-    const int64_t *dst_ptr;     // [sh_rows + 1] CSR: where (in sendbuf) the partial force of a shared row goes
-    const int32_t *dst_pos;
-    const int64_t *src_ptr;     // [sh_rows + 1] CSR: sources (into xbuf) of a shared row, ASCENDING holder rank
-    const int32_t *src_pos;
+    double *xbuf;               // [sh_rows] own partial forces of the shared rows
+    double *sendbuf;            // packed messages to all neighbours, concatenated (NCCL / group / host transports)
+    const double *recv;         // received partial forces of all neighbours, concatenated like sendbuf
+    int64_t recv_stride;        // peer transport: the receive area is double-buffered, parity p lives at recv + p*stride
+    const int64_t *dst_ptr;     // [sh_rows + 1] CSR: where the partial force of a shared row goes ...
+    const int32_t *dst_pos;     //   position inside sendbuf (or, peer transport, inside the neighbour's receive area)
+    const int32_t *dst_nb;      //   neighbour index k of that destination
+    const int64_t *src_ptr;     // [sh_rows + 1] CSR: sources of a shared row, ASCENDING holder rank:
+    const int32_t *src_pos;     //   < sh_rows: xbuf[src_pos]; otherwise recv[src_pos - sh_rows]
+    // peer-memory transport over NVLink (one process per GPU, cudaIpc-mapped receive areas)
+    int n_nb;
+    double *const *peer_recv;               // [n_nb] base of neighbour k's receive area (mapped peer memory)
+    const int64_t *peer_stride;             // [n_nb] its parity stride (the neighbour's total message length)
+    unsigned long long *const *peer_flag;   // [n_nb] the neighbour's arrival flag for messages from this rank
+    const unsigned long long *flags;        // [n_nb] local arrival flags, flag[k] = number of messages received from k
+    unsigned int *done_ctr;                 // blocks of the pack kernel that have finished (last one raises the flags)
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
@@ -127,16 +155,20 @@ __device__ __forceinline__ void saa_finish_row(const SaaDev &P, int64_t slice, i
 // K1: fused force + update over slices [slice_begin, slice_end).  One warp per slice.
 //   ADD_ZERO: the synchronised path routes every force through f_global = 0; f_global += f
 //             (Distributed_tools.py:84-86), i.e. F_int = 0.0 + s; the local path uses s itself.
-// d1 overwrites dn in place (row i only needs its own dn[i]).  tn is read from device memory so that
-// the launch can be replayed from a CUDA graph; block 0 writes tn + dt for the next step (:235).
+// d1 overwrites dn in place (row i only needs its own dn[i]).  The clock is read from device memory so that
+// the launch can be replayed from a CUDA graph; block 0 writes tn + dt for the next step (:235) and, on the
+// synchronised path, counts the step.
 template <bool ADD_ZERO>
 __global__ void __launch_bounds__(256) saa_k_step(SaaDev P, int64_t slice_begin, int64_t slice_end, const double *__restrict__ d0,
-                                                  double *__restrict__ dn_d1, const double *tn_in, double *tn_out)
+                                                  double *__restrict__ dn_d1, const SaaClock *clk_in, SaaClock *clk_out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t slice = slice_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const double tn = *tn_in;
-    if (tn_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *tn_out = __dadd_rn(tn, P.dt);
+    const double tn = clk_in->tn;
+    if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        clk_out->tn = __dadd_rn(tn, P.dt);
+        clk_out->sync_step = clk_in->sync_step + (ADD_ZERO ? 1ull : 0ull);
+    }
     if (slice >= slice_end) return;
     double s = saa_row_dot<8, true>(P, slice, lane, d0);
     if (ADD_ZERO) s = __dadd_rn(0.0, s);
@@ -145,27 +177,69 @@ __global__ void __launch_bounds__(256) saa_k_step(SaaDev P, int64_t slice_begin,
 
 // K2: partial internal force of the shared rows, stored for the own sum and packed into the messages
 // of every neighbour holding the node (fused halo pack).
-__global__ void __launch_bounds__(256) saa_k_boundary(SaaDev P, SaaHaloDev H, const double *__restrict__ d0)
+//   PEER: the message entries are stored straight into the neighbours' receive areas over NVLink (mapped peer
+//   memory, parity = sync_step & 1); the last block to finish publishes "message sync_step+1 has arrived" to
+//   every neighbour with a system-scope release store.
+template <bool PEER>
+__global__ void __launch_bounds__(256) saa_k_boundary(SaaDev P, SaaHaloDev H, const double *__restrict__ d0, const SaaClock *clk_in)
 {
     const int lane = threadIdx.x & 31;
     const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (slice >= P.sh_slices) return;
-    const double s = saa_row_dot<8, true>(P, slice, lane, d0);
-    const int64_t row = slice * 32 + lane;
-    H.xbuf[row] = s;
-    for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) H.sendbuf[H.dst_pos[k]] = s;
+    unsigned long long step = 0;
+    if (PEER) step = clk_in->sync_step;
+    if (slice < P.sh_slices) {
+        const double s = saa_row_dot<8, true>(P, slice, lane, d0);
+        const int64_t row = slice * 32 + lane;
+        H.xbuf[row] = s;
+        for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+            if (PEER) {
+                const int nb = H.dst_nb[k];
+                H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s;
+            } else {
+                H.sendbuf[H.dst_pos[k]] = s;
+            }
+        }
+    }
+    if (PEER) {
+        __threadfence_system();                      // this thread's peer stores are visible system-wide ...
+        __syncthreads();                             // ... before thread 0 counts the block as done
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(H.done_ctr, 1u);
+            if (t == gridDim.x - 1) {
+                *H.done_ctr = 0u;                    // re-arm for the next step (next launch is stream-ordered)
+                __threadfence_system();
+                for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
+            }
+        }
+    }
 }
 
 // K3: fused halo unpack + rank-ordered sum + update of the shared rows:
 //   F_int = ((0.0 + f_r0) + f_r1) + ...   holders r0 < r1 < ... (Distributed_tools.py:84-86)
+//   PEER: first wait (acquire, system scope) until every neighbour's message of this step has arrived.
+template <bool PEER>
 __global__ void __launch_bounds__(256) saa_k_shared_update(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
-                                                           double *__restrict__ dn_d1, const double *tn_in)
+                                                           double *__restrict__ dn_d1, const SaaClock *clk_in)
 {
+    const double *recv = H.recv;
+    if (PEER) {
+        const unsigned long long step = clk_in->sync_step;
+        if (threadIdx.x < H.n_nb) {
+            while (ld_acquire_sys_u64(H.flags + threadIdx.x) < step + 1ull) __nanosleep(64);
+        }
+        __syncthreads();
+        recv += (int64_t)(step & 1ull) * H.recv_stride;
+    }
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= H.sh_rows) return;
     double Fi = 0.0;
-    for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) Fi = __dadd_rn(Fi, H.xbuf[H.src_pos[k]]);
-    saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(*tn_in));
+    for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+        const int32_t s = H.src_pos[k];
+        // received entries were written by another GPU during this launch sequence: plain (coherent) loads
+        const double v = (s < H.sh_rows) ? H.xbuf[s] : *((const volatile double *)(recv + (s - H.sh_rows)));
+        Fi = __dadd_rn(Fi, v);
+    }
+    saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(clk_in->tn));
 }
 
 // syn_cpus as a stand-alone operation (Distributed_tools.py:77-92) on a caller-provided force vector:
@@ -185,7 +259,10 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
     if (row >= n_rows) return;
     double Fi = 0.0;
     if (row < H.sh_rows) {
-        for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) Fi = __dadd_rn(Fi, H.xbuf[H.src_pos[k]]);
+        for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+            const int32_t s = H.src_pos[k];
+            Fi = __dadd_rn(Fi, (s < H.sh_rows) ? H.xbuf[s] : H.recv[s - H.sh_rows]);
+        }
     } else {
         Fi = __dadd_rn(Fi, f[row]);
     }
@@ -195,14 +272,14 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
 // Persistent variant of K1 (local mode): one cooperative launch runs n_steps time steps; u stays in HBM/L2,
 // the two displacement buffers swap roles after each grid-wide barrier.  tn advances in registers with the
 // same sequence of additions as the host loop (Data_prepare.py:235).
-__global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, double *bufB, double *tn_io,
+__global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, double *bufB, SaaClock *clk_io,
                                                         int64_t n_steps)
 {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    double tn = *tn_io;
+    double tn = clk_io->tn;
     double *d0 = bufA, *dn = bufB;
     for (int64_t step = 0; step < n_steps; ++step) {
         const double ramp = saa_ramp(tn);
@@ -214,7 +291,7 @@ __global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, 
         double *t = d0; d0 = dn; dn = t;
         grid.sync();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *tn_io = tn;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clk_io->tn = tn;
 }
 
 // ---- small data-movement kernels -----------------------------------------------------------------------

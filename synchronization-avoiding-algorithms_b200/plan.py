@@ -62,6 +62,8 @@ ABI = {
     "saa_group_step": (_int, [_vp, _i64, _int, _int]),
     "saa_group_synchronize": (_int, [_vp]),
     "saa_group_destroy": (_int, [_vp]),
+    "saa_plan_peer_export": (_int, [_vp, _vp, _vp]),
+    "saa_plan_peer_attach": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "saa_nccl_unique_id": (_int, [_vp]),
     "saa_plan_init_nccl": (_int, [_vp, _vp]),
 }
@@ -290,6 +292,31 @@ class StepPlan:
         out = np.empty(self.n_dof)
         _check(lib().saa_plan_forces_end_host(self.h, _p(recv), _p(out)), "saa_plan_forces_end_host")
         return out
+
+    # ---- peer-memory transport (NVLink, one process per GPU) ----------------------------------------
+    def peer_export(self):
+        """(64-byte CUDA IPC handle of the receive area, neighbour ranks, message offsets)."""
+        buf = ctypes.create_string_buffer(64)
+        tot = ctypes.c_int64(0)
+        _check(lib().saa_plan_peer_export(self.h, buf, ctypes.byref(tot)), "saa_plan_peer_export")
+        nb, off = self.halo_layout()
+        return dict(rank=self.rank, handle=buf.raw, nb=nb.tolist(), off=off.tolist())
+
+    def peer_attach(self, exports):
+        """exports: list over ALL ranks of peer_export() dicts (e.g. from all_gather_object)."""
+        nb, off = self.halo_layout()
+        by_rank = {e["rank"]: e for e in exports if e is not None}
+        handles = b""
+        r_off, r_tot, r_slot, r_nnb = [], [], [], []
+        for r in nb.tolist():
+            e = by_rank[r]
+            slot = e["nb"].index(self.rank)
+            handles += e["handle"]
+            r_off.append(e["off"][slot]); r_tot.append(e["off"][-1]); r_slot.append(slot); r_nnb.append(len(e["nb"]))
+        hb = ctypes.create_string_buffer(handles, max(len(handles), 1))
+        a = lambda v, t: np.ascontiguousarray(v, dtype=t)
+        ro, rt, rs, rn = a(r_off, np.int64), a(r_tot, np.int64), a(r_slot, np.int32), a(r_nnb, np.int32)
+        _check(lib().saa_plan_peer_attach(self.h, nb.size, hb, _p(ro), _p(rt), _p(rs), _p(rn)), "saa_plan_peer_attach")
 
     # ---- NCCL transport ----------------------------------------------------------------------------
     def init_nccl(self, unique_id: bytes):

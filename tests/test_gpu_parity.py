@@ -233,3 +233,29 @@ def test_errors_are_reported():
     p0 = splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g2["dt"], 0.5, halo=maps.halo_plan(0, 2, lists), rank=0, size=2)
     with pytest.raises(splan.SaaError):
         p0.step(1, splan.MODE_SYNC)                        # no transport attached
+
+
+def _ngpu():
+    try:
+        return splan.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("name,n", [("beam_coarse_P2", 2), ("beam_coarse_P4", 4), ("beam_coarse_P8", 8)])
+def test_one_process_per_gpu_transports(transport, name, n):
+    """N GPUs of one box, one process each: NVLink peer-memory stores / NCCL send-recv reproduce the
+    reference's syn_cpus histories bit for bit (skipped when the box has fewer GPUs)."""
+    import os
+    import subprocess
+    import sys
+    if _ngpu() < n:
+        pytest.skip(f"needs {n} GPUs")
+    from util import ROOT
+    port = 29600 + (os.getpid() + 13 * n) % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), transport, name]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(f"ok ({transport})") == n
