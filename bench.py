@@ -2,21 +2,21 @@
 """bench.py — DOF-steps/s of the explicit FE time step on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--m M] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE explicit time step (one pass of Dynamic_solver.py:9-34 over the whole mesh):
-force K.u, central-difference update, Dirichlet clamp and — for N > 1 — the shared-node force exchange.
-Workload (config.workload): the 25 x 1 x 1 cantilever of Mesh_info/beam_US.geo as a structured tet mesh
-with m cells per unit length; m = 24 -> 1.13 M DOF (BASELINE config 2, "~1M DOF, single B200, fp64").
-For N > 1 the same mesh is partitioned over the N GPUs (one process per GPU, halo exchange over NCCL).
+A "step" is ONE explicit time step (one pass of Dynamic_solver.py:9-34 over the whole mesh): force K.u,
+central-difference update, Dirichlet clamp and — for N > 1 — the shared-node force exchange.
+Workload (config.workload): the 25 x 1 x 1 cantilever of Mesh_info/beam_US.geo as a structured tet mesh with
+m cells per unit length.  Defaults follow BASELINE.json's configs: one GPU -> m = 24 (1.13 M DOF, "~1M DOF,
+single B200, fp64"); N > 1 -> m = 65 (21.2 M DOF, "~20M DOF over 2/4/8 B200") cut into N x-slabs, one
+process per GPU, shared-node forces exchanged every step.  --m 111 is the 104 M-DOF mesh of the 100M sweep.
 
-`value`  : whole-job DOF-steps/s with the state resident in HBM (CUDA events on the plan's stream).
-`e2e`    : the same metric through the reference-facing call saa_step_host — one
-           parallel_explicit_solver_dis_pre evaluation per call with (d0, dn) in pinned HOST memory
-           and d1 returned to HOST memory, copies inside the timed region.
-`roofline`: algorithmic bytes of the fused force+update kernel (12 B per stored entry
-           + 4 B per row pointer + five fp64 vector streams) / average step time, vs the measured
-           HBM copy bandwidth of MEASURED_PEAKS.json.
-`cpu_baseline`: the CPU oracle (oracle/fem_oracle.c, OpenMP) on the same problem on the host cores.
+`value`   whole-job DOF-steps/s with the state resident in HBM (CUDA events on the plan's stream, max over ranks).
+`e2e`     the same metric through the reference-facing call saa_step_host — one parallel_explicit_solver_dis_pre
+          evaluation per call with (d0, dn) in pinned HOST memory and d1 returned to HOST memory every step.
+`roofline` algorithmic bytes of the fused force+update kernel (12 B per stored entry + 4 B per
+          row pointer + five fp64 vector streams) / average step time, vs the measured HBM copy bandwidth.
+`cpu_baseline` the CPU oracle (oracle/fem_oracle.c, OpenMP) on the same problem on the box's host cores.
 """
 import argparse
 import json
@@ -24,7 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,20 +35,30 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=0, help="timed time steps (0: 10000 for m <= 32, else 2000)")
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--m", type=int, default=0, help="cells per unit length of the 25x1x1 beam (0: default for N)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed host-call steps (0: 200 for m <= 32, else 30)")
     ap.add_argument("--launch", default="auto", choices=["auto", "per_step", "graph", "persistent"])
+    ap.add_argument("--setup", default="device", choices=["device", "host"], help="where the problem is assembled")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="N = 1: skip the extra 21 M-DOF measurement")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo transport for N > 1")
     return ap.parse_args()
 
 
 def default_m(n_gpus):
-    return 24  # 1.13 M DOF (config 2); the same mesh is strong-scaled over N GPUs
+    """BASELINE.json configs: one B200 -> ~1M DOF (m = 24: 1 126 875 DOF); 2/4/8 B200 -> ~20M DOF (m = 65:
+    21 215 700 DOF) partitioned over the GPUs.  --m overrides (m = 111: 104 M DOF, the 100M-DOF sweep)."""
+    return 24 if n_gpus == 1 else 65
+
+
+def workload_name(m, n_dof, n_el):
+    cfg = {24: "BASELINE config 2 (~1M DOF, single B200, fp64)", 65: "BASELINE config 3 (~20M DOF over 2/4/8 B200)",
+           111: "BASELINE config 4 (~100M DOF strong-scaling sweep)"}.get(m, "custom refinement")
+    return f"structured 25x1x1 cantilever (Mesh_info/beam_US.geo box) m={m}: {n_dof} DOF, {n_el} tets; {cfg}"
 
 
 def measured_peak():
@@ -103,85 +112,113 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+            # median over the samples taken under load (power above half of the maximum seen)
+            busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
                        reasons=sorted(reasons), samples=len(sm))
         return out
 
 
-def build_rank_problem(m, size, rank):
-    """Mesh, partition and this rank's assembled inputs (host side; see saa_b200.problem)."""
-    import pickle
+# ---- problem set-up -------------------------------------------------------------------------------------------
+def setup_host(m, size, rank, local, make_plan=True):
+    """Host set-up (bit-exact with the reference's own assembly): numpy/scipy, METIS partition for N > 1."""
     import saa_b200  # noqa: F401
     from saa_b200 import mesh, partition, problem
-    cache = os.environ.get("SAA_BENCH_CACHE")       # optional: reuse the assembled problem across runs of one session
-    cfile = os.path.join(cache, f"pb_m{m}_P{size}_r{rank}.pkl") if cache else None
-    if cfile and os.path.isfile(cfile):
-        with open(cfile, "rb") as fh:
-            return pickle.load(fh)
     pts, cells, fac = mesh.structured_beam(m)
     if size == 1:
-        ep = np.zeros(len(cells), dtype=np.int64)
-        part = "none"
-    elif len(cells) <= 3_000_000:
-        ep = partition.metis_part_mesh(cells, len(pts), size)
-        part = "METIS_PartMeshDual(ncommon=3)"
+        ep, part = np.zeros(len(cells), dtype=np.int64), "none"
     else:
-        ep = partition.slab_partition(pts, cells, size)
-        part = "x-slabs"
+        ep, part = partition.metis_part_mesh(cells, len(pts), size), "METIS_PartMeshDual(ncommon=3)"
     pb = problem.build_problem(pts, cells, fac, ep, size, ranks=[rank])
-    out = (pb, part, len(pts), len(cells))
-    if cfile:
-        os.makedirs(cache, exist_ok=True)
-        with open(cfile, "wb") as fh:
-            pickle.dump(out, fh, protocol=4)
-    return out
+    q = pb["ranks"][rank]
+    pl = problem.make_plan(q, pb["dt"], problem.DAMP_DEFAULT, size, device=local) if make_plan else None
+    csr = dict(K=q["K"], F=q["F"], lM=q["lM"], dirichlet=q["dirichlet"], nodes=q["nodes"])
+    return pl, dict(dt=float(pb["dt"]), n_nodes=len(pts), n_elem=len(cells), part=part, csr=csr,
+                    assembly="host (numpy/scipy, bit-exact with the reference's assembly)")
 
 
-def oracle_for(pb, rank_ids, n_nodes):
+def setup_device(m, size, rank, local, keep_csr=False):
+    """Device set-up (saa_b200.device_setup): slab mesh, numbering, K6 assembly and the plan, all on the GPU."""
+    import saa_b200  # noqa: F401
+    from saa_b200 import device_setup
+    pl, info = device_setup.build_structured_rank(m, rank, size, device_index=local, keep_csr=keep_csr)
+    csr = None
+    if keep_csr:
+        csr = dict(K=info["K"].to_scipy(), F=info["F"].cpu().numpy(), lM=info["lM"].cpu().numpy(), dirichlet=info["dirichlet"],
+                   nodes=info["local_nodes"].cpu().numpy())
+        info["K"].free()
+    return pl, dict(dt=float(info["dt"]), n_nodes=info["n_global_nodes"], n_elem=info["n_global_elem"],
+                    part="none" if size == 1 else f"{size} x-slabs of whole hexahedron layers (what a k-way cut of a 25:1:1 beam gives)",
+                    csr=csr, assembly="device (saa_assemble_stiffness_dev, closed-form element matrices)")
+
+
+def oracle_for(csr, n_nodes, dt):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fem_oracle
-    ranks = [dict(K_indptr=pb["ranks"][r]["K"].indptr, K_indices=pb["ranks"][r]["K"].indices,
-                  K_data=pb["ranks"][r]["K"].data, F=pb["ranks"][r]["F"], lM=pb["ranks"][r]["lM"],
-                  dirichlet=pb["ranks"][r]["dirichlet"], nodes=pb["ranks"][r]["nodes"]) for r in rank_ids]
-    return fem_oracle.OracleProblem(n_nodes, ranks, pb["dt"], 0.5)
+    K = csr["K"]
+    ranks = [dict(K_indptr=K.indptr, K_indices=K.indices, K_data=K.data, F=csr["F"], lM=csr["lM"], dirichlet=csr["dirichlet"],
+                  nodes=csr["nodes"])]
+    return fem_oracle.OracleProblem(n_nodes, ranks, dt, 0.5)
 
 
-def cpu_baseline(pb, n_nodes, seconds, start_state=None):
+def cpu_baseline(csr, n_nodes, dt, seconds):
     """Time the C oracle (all OpenMP threads) on the SAME serial problem for a bounded number of steps."""
-    o = oracle_for(pb, [0], n_nodes)
-    if start_state is not None:
-        o.set_state(0, *start_state)
-    n_dof = pb["ranks"][0]["F"].size
+    o = oracle_for(csr, n_nodes, dt)
+    n_dof = csr["F"].size
     o.run(2)                                  # warm
     t0 = time.perf_counter(); o.run(1); t1 = time.perf_counter() - t0
     k = int(max(3, min(2000, seconds / max(t1, 1e-6))))
-    t0 = time.perf_counter(); o.run(k); dt_ = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.run(k); secs = time.perf_counter() - t0
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     threads = int(os.environ.get("OMP_NUM_THREADS", cores))
     o.close()
-    return dict(value=n_dof * k / dt_, unit="DOF-steps/s", cores=threads, kind="port",
+    return dict(value=n_dof * k / secs, unit="DOF-steps/s", cores=threads, kind="port",
                 sample=f"{k} consecutive time steps of the same {n_dof}-DOF mesh with oracle/fem_oracle.c (OpenMP over rows, "
-                       f"{threads} threads); the reference itself is single-threaded numpy/scipy per MPI rank"), k, dt_
+                       f"{threads} threads); the reference itself is single-threaded numpy/scipy per MPI rank"), k, secs
 
 
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference's own path on the host cores (the reference is
-    Python and is not present on the GPU box; oracle/fem_oracle.c is its pinned, bit-exact port)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    Python and does not exist on the GPU box; oracle/fem_oracle.c is its pinned, bit-exact port).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)   # torchrun pins it to 1; the baseline may use every core
     m = args.m or default_m(args.gpus)
-    pb, part, n_nodes, n_el = build_rank_problem(m, 1, 0)
-    cb, k, secs = cpu_baseline(pb, n_nodes, max(args.cpu_seconds, 20.0))
+    csr = None
+    if m > 32:
+        try:                                   # inputs of the CPU run come from the device assembly (host one would take minutes)
+            pl, info = setup_device(m, 1, 0, 0, keep_csr=True)
+            csr, n_nodes, n_el, dt = info["csr"], info["n_nodes"], info["n_elem"], info["dt"]
+            pl.close()
+        except Exception as e:                 # no GPU: fall through to the host assembly
+            print(f"[bench] device set-up unavailable for the reference arm ({e}); assembling on the host", file=sys.stderr)
+    if csr is None:
+        _, info = setup_host(m, 1, 0, 0, make_plan=False)
+        csr, n_nodes, n_el, dt = info["csr"], info["n_nodes"], info["n_elem"], info["dt"]
+    cb, k, secs = cpu_baseline(csr, n_nodes, dt, max(args.cpu_seconds, 20.0))
     n_dof = 3 * n_nodes
     line = {"impl": "reference", "metric": "DOF-steps/sec", "value": cb["value"], "unit": "DOF-steps/s",
             "n_gpus": args.gpus, "steps": k, "warmup": 3, "ms_per_step": 1e3 * secs / k, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"structured 25x1x1 cantilever m={m}: {n_dof} DOF, {n_el} tets (BASELINE config 2)",
-                       "note": f"requested --steps {args.steps} bounded to {k} CPU time steps of the full mesh"},
+            "config": {"workload": workload_name(m, n_dof, n_el),
+                       "note": f"requested --steps {args.steps or 'default'} bounded to {k} CPU time steps of the full mesh"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "DOF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def time_resident(pl, torch, stream, steps, warmup, mode, launch, barrier):
+    pl.step(warmup, mode, launch)
+    pl.synchronize()
+    barrier()
+    l0 = pl.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    pl.step(steps, mode, launch)
+    e1.record(stream)
+    pl.synchronize()
+    barrier()
+    return e0.elapsed_time(e1), pl.kernel_launches - l0
 
 
 def main():
@@ -192,14 +229,13 @@ def main():
     import torch
     import torch.distributed as dist
     import saa_b200  # noqa: F401
-    from saa_b200 import multi, plan as splan, problem
+    from saa_b200 import multi, plan as splan
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the time-step path has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -207,14 +243,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     m = args.m or default_m(world)
+    steps = args.steps or (10000 if m <= 32 else 2000)
+    e2e_steps = args.e2e_steps or (200 if m <= 32 else 30)
+    want_cpu = (not args.no_cpu_baseline) and world == 1
     t_setup = time.time()
-    pb, part, n_nodes, n_el = build_rank_problem(m, world, rank)
-    q = pb["ranks"][rank]
-    pl = problem.make_plan(q, pb["dt"], problem.DAMP_DEFAULT, world, device=local)
+    if args.setup == "host":
+        pl, info = setup_host(m, world, rank, local)
+    else:
+        pl, info = setup_device(m, world, rank, local, keep_csr=want_cpu and m <= 32)
     transport = multi.attach_transport(pl, args.transport) if world > 1 else "none"
     t_setup = time.time() - t_setup
-    n_dof_global = 3 * n_nodes
+    n_dof_global = 3 * info["n_nodes"]
     n_dof_local = pl.n_dof
+    dtv = info["dt"]
     mode = splan.MODE_SYNC if world > 1 else splan.MODE_LOCAL
     launch = {"auto": splan.LAUNCH_AUTO, "per_step": splan.LAUNCH_PER_STEP, "graph": splan.LAUNCH_GRAPH,
               "persistent": splan.LAUNCH_PERSISTENT}[args.launch]
@@ -225,93 +266,96 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident timing --------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
-    pl.step(args.warmup, mode, launch)
-    pl.synchronize()
-    barrier()
-    l0 = pl.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    pl.step(args.steps, mode, launch)
-    e1.record(stream)
-    pl.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = pl.kernel_launches - l0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, launches = time_resident(pl, torch, stream, steps, args.warmup, mode, launch, barrier)
+    ms = max_over_ranks(ms)
 
     # ---- end to end through the reference-facing host call -----------------------------------------
     d0, dn, tn = pl.get_state()
     h0 = torch.from_numpy(d0).pin_memory().numpy()
     hn = torch.from_numpy(dn).pin_memory().numpy()
     h1 = torch.empty(n_dof_local, dtype=torch.float64).pin_memory().numpy()
-    dtv = float(pb["dt"])
     for _ in range(3):
         pl.step_host(h0, hn, tn, mode, out=h1)
     barrier()
     w0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         pl.step_host(h0, hn, tn, mode, out=h1)       # d1 lands in host memory every call
         h0, hn, h1 = h1, h0, hn                      # d_n = d_0; d_0 = d1 (Data_prepare.py:233-234)
         tn = tn + dtv
-    e1.record(stream)
     pl.synchronize()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    wall_e2e = (time.perf_counter() - w0) * 1e3
-    t = torch.tensor([max(ms_e2e, wall_e2e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks((time.perf_counter() - w0) * 1e3)   # the call is synchronous: wall clock covers copies + kernels
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline of the fused force+update kernel (local sizes of this rank; max time over ranks) ---
+    # ---- roofline of the fused force+update kernel (largest shard bounds the step) ------------------
     nnz = pl.nnz
-    alg_bytes = nnz * 12 + (n_dof_local + 1) * 4 + 5 * 8 * n_dof_local
-    sums = torch.tensor([float(alg_bytes), float(nnz), float(n_dof_local)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.MAX)       # the slowest rank bounds the step: use the largest shard
-    alg_bytes_max = float(sums[0].item())
-    step_s = ms * 1e-3 / args.steps
+    alg_bytes = max_over_ranks(float(nnz * 12 + (n_dof_local + 1) * 4 + 5 * 8 * n_dof_local))
+    step_s = ms * 1e-3 / steps
     peak, peak_src = measured_peak()
-    achieved = alg_bytes_max / step_s / 1e9
+    achieved = alg_bytes / step_s / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if os.path.isfile(tf):
+    if os.path.isfile(tf) and m == 24 and world == 1:
         try:
             traffic = json.load(open(tf)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
 
+    also = None
+    if world == 1 and m == 24 and not args.no_also and args.setup == "device":
+        # the strong-scaling base: BASELINE config 3's 21 M-DOF mesh on this one GPU
+        try:
+            pl2, info2 = setup_device(65, 1, 0, local)
+            st2 = torch.cuda.ExternalStream(pl2.stream, device=torch.device("cuda", local))
+            ms2, _ = time_resident(pl2, torch, st2, 1000, 50, splan.MODE_LOCAL, launch, barrier)
+            b2 = pl2.nnz * 12 + (pl2.n_dof + 1) * 4 + 40 * pl2.n_dof
+            also = {"workload": workload_name(65, 3 * info2["n_nodes"], info2["n_elem"]), "steps": 1000,
+                    "value": 3 * info2["n_nodes"] * 1000 / (ms2 * 1e-3), "ms_per_step": ms2 / 1000,
+                    "roofline_frac": b2 / (ms2 * 1e-6) / 1e9 / peak, "nnz_per_row": pl2.nnz / pl2.n_dof}
+            pl2.close()
+        except Exception as e:
+            also = {"error": str(e)[:200]}
+
     if rank == 0:
         line = {
-            "metric": "DOF-steps/sec", "value": n_dof_global * args.steps / (ms * 1e-3), "unit": "DOF-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": "DOF-steps/sec", "value": n_dof_global * steps / (ms * 1e-3), "unit": "DOF-steps/s",
+            "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"structured 25x1x1 cantilever (Mesh_info/beam_US.geo box) m={m}: {n_dof_global} DOF, "
-                                   f"{n_el} tets; BASELINE config 2 (~1M DOF, fp64)",
-                       "partition": part, "transport": transport, "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
+            "config": {"workload": workload_name(m, n_dof_global, info["n_elem"]),
+                       "partition": info["part"], "transport": transport, "assembly": info["assembly"],
+                       "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
                        "launch": args.launch, "dt": dtv, "setup_s": round(t_setup, 1),
-                       "l2": "inputs larger than L2: matrix stream per step = %.0f MB vs 126 MB L2" % (pl.matrix_bytes / 1e6)},
-            "e2e": {"value": n_dof_global * args.e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",
+                       "l2": "inputs larger than L2: matrix stream per step per GPU = %.0f MB vs 126 MB L2" % (pl.matrix_bytes / 1e6)},
+            "e2e": {"value": n_dof_global * e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",
                     "h2d_bytes_per_step": 2 * 8 * n_dof_local, "d2h_bytes_per_step": 8 * n_dof_local,
-                    "steps": args.e2e_steps, "ms_per_step": ms_e2e / args.e2e_steps,
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "call": "saa_step_host (one parallel_explicit_solver_dis_pre evaluation per call, pinned host d0/dn in, d1 out)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_launch": alg_bytes_max, "bytes_formula": "12*nnz + 4*(rows+1) + 40*rows",
+                         "bytes_per_launch": alg_bytes, "bytes_formula": "12*nnz + 4*(rows+1) + 40*rows (largest shard)",
                          "stored_bytes_per_launch": pl.matrix_bytes + 40 * n_dof_local,
                          "kernel": "saa_k_step (fused K.u + central-difference update + Dirichlet mask)"},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
-            cb, _, _ = cpu_baseline(pb, n_nodes, args.cpu_seconds)
+        if also is not None:
+            line["also"] = also
+        if want_cpu:
+            csr = info["csr"]
+            if csr is None:     # large mesh: time the CPU on the 1.13 M-DOF mesh instead (DOF-normalised metric)
+                _, i24 = setup_host(24, 1, 0, local, make_plan=False)
+                csr, nn, dt24 = i24["csr"], i24["n_nodes"], i24["dt"]
+            else:
+                nn, dt24 = info["n_nodes"], dtv
+            cb, _, _ = cpu_baseline(csr, nn, dt24, args.cpu_seconds)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:

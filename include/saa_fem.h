@@ -89,6 +89,40 @@ int saa_plan_set_halo(saa_plan *plan, int rank, int size, int64_t n_shared, cons
                       int n_nb, const int32_t *nb_rank, const int64_t *nb_ptr, const int64_t *send_idx,
                       const int64_t *holders_ptr, const int32_t *holders_rank, const int64_t *holders_slot);
 
+/*
+ * Same as saa_plan_create for inputs that already live on the plan's GPU (set-up at scale, see
+ * saa_assemble_stiffness_dev): LocalK as CSR with int64 indptr, int32 sorted indices, float64 data; F_rankwise
+ * and l_M as (n_dof) device vectors.  `dirichlet` is a host list.  The device arrays are borrowed until
+ * saa_plan_finalize returns (which builds the same layout as the host path, entirely on the GPU); the caller
+ * may free them afterwards.
+ */
+int saa_plan_create_dev(saa_plan **out, int device, int64_t n_dof, const int64_t *indptr_dev, const int32_t *indices_dev,
+                        const double *data_dev, const double *F_rankwise_dev, const double *l_M_dev,
+                        const int64_t *dirichlet_host, int64_t n_dirichlet, double dt, double dt2, double dt_half,
+                        double half_alpha, double alpha);
+
+/*
+ * Sparse assembly on the GPU — Local_assembly_for_stiffness (Tools/Mat_construction.py:122-150) without the
+ * dense (3n)^2 accumulator.  cells_dev: (n_elem,4) int32 LOCAL node ids of the rank's elements in
+ * Local_ele_list order; coords_dev: (n_nodes,3) coordinates in Local_nodal_list order.  Returns cudaMalloc'ed
+ * CSR arrays (3*n_nodes rows, int64 indptr, int32 ascending columns, exact zeros dropped); release them with
+ * saa_device_free.  Element contributions are added in ascending element order by the thread owning the row
+ * (deterministic, no atomics).  Values agree with the reference's BLAS-evaluated B^T D B to a few 1e-16
+ * relative, not bit for bit.
+ */
+int saa_assemble_stiffness_dev(int device, int64_t n_nodes, int64_t n_elem, const int32_t *cells_dev,
+                               const double *coords_dev, double lmd, double mu, int64_t **indptr_out_dev,
+                               int32_t **indices_out_dev, double **data_out_dev, int64_t *nnz_out);
+/* Row-summed (lumped) mass per node and un-ramped load vector (3 per node) of the LOCAL elements only
+ * (Local_MKF, Mat_construction.py:36-73; lumping_to_vec, commons.py:103-107); shared nodes still need the
+ * sum over their holders.  Outputs are caller-allocated device arrays of n_nodes and 3*n_nodes doubles. */
+int saa_assemble_mass_load_dev(int device, int64_t n_nodes, int64_t n_elem, const int32_t *cells_dev,
+                               const double *coords_dev, double rho, double fz, double *m_node_out_dev,
+                               double *F_out_dev);
+int saa_device_free(void *ptr);
+/* cudaMemcpy(dst, src, bytes, cudaMemcpyDefault) — lets bindings read the arrays above */
+int saa_device_copy(void *dst, const void *src, int64_t bytes);
+
 /* Upload everything to the GPU (boundary-first row order, sliced-ELL storage). */
 int saa_plan_finalize(saa_plan *plan);
 int saa_plan_destroy(saa_plan *plan);

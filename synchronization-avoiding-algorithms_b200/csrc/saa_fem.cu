@@ -91,6 +91,11 @@ static int load_nccl()
 struct saa_plan {
     int device = 0;
     bool finalized = false;
+    // device-resident inputs (saa_plan_create_dev): borrowed until finalize
+    bool dev_input = false;
+    const int64_t *in_indptr = nullptr;
+    const int32_t *in_indices = nullptr;
+    const double *in_data = nullptr, *in_F = nullptr, *in_M = nullptr;
     // host copies of the inputs (released by finalize)
     int64_t n_dof = 0;
     std::vector<int32_t> indptr, indices;
@@ -252,10 +257,14 @@ static void sigma_sort(std::vector<int64_t> &rows, const std::vector<int32_t> &i
     }
 }
 
+static int finalize_tail(saa_plan *p, int64_t sh_pad);
+static int finalize_device(saa_plan *p);
+
 extern "C" int saa_plan_finalize(saa_plan *p)
 {
     if (!p) return fail("saa_plan_finalize: null plan");
     if (p->finalized) return 0;
+    if (p->dev_input) return finalize_device(p);
     CK(cudaSetDevice(p->device));
     const int64_t n = p->n_dof;
     const int64_t n_shared = (int64_t)p->shared_pos.size();
@@ -332,6 +341,15 @@ extern "C" int saa_plan_finalize(saa_plan *p)
     if (upload(&p->d_slice_ptr, slice_ptr) || upload(&p->d_val, val) || upload(&p->d_col, col) ||
         upload(&p->d_M, M) || upload(&p->d_F, F) || upload(&p->d_dir, dir) || upload(&p->d_iperm, p->iperm_h))
         return -1;
+    return finalize_tail(p, sh_pad);
+}
+
+// second half of finalize, shared by the host-CSR and the device-CSR paths: state buffers, kernel parameter
+// block, halo tables.  Needs n_rows / n_slices / sh_slices / iperm_h and the device layout arrays.
+static int finalize_tail(saa_plan *p, int64_t sh_pad)
+{
+    const int64_t n = p->n_dof;
+    const int64_t n_shared = (int64_t)p->shared_pos.size();
     for (int b = 0; b < 2; ++b) {
         CK(cudaMalloc((void **)&p->d_buf[b], p->n_rows * sizeof(double)));
         CK(cudaMemset(p->d_buf[b], 0, p->n_rows * sizeof(double)));
@@ -1071,3 +1089,5 @@ extern "C" int saa_plan_init_nccl(saa_plan *p, const void *id128)
     NCK(g_nccl.CommInitRank(&p->comm, p->size, id, p->rank));
     return 0;
 }
+
+#include "saa_device_setup.cuh"

@@ -32,6 +32,11 @@ ABI = {
     "saa_last_error": (ctypes.c_char_p, []),
     "saa_device_count": (_int, []),
     "saa_plan_create": (_int, [_PP, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64]),
+    "saa_plan_create_dev": (_int, [_PP, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64]),
+    "saa_assemble_stiffness_dev": (_int, [_int, _i64, _i64, _vp, _vp, _f64, _f64, _PP, _PP, _PP, _vp]),
+    "saa_assemble_mass_load_dev": (_int, [_int, _i64, _i64, _vp, _vp, _f64, _f64, _vp, _vp]),
+    "saa_device_free": (_int, [_vp]),
+    "saa_device_copy": (_int, [_vp, _vp, _i64]),
     "saa_plan_set_halo": (_int, [_vp, _int, _int, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "saa_plan_finalize": (_int, [_vp]),
     "saa_plan_destroy": (_int, [_vp]),
@@ -148,6 +153,27 @@ class StepPlan:
                                  _p(F), _p(M), _p(D), D.size, self.dt, self.dt2, self.dt_half, self.half_alpha,
                                  self.alpha), "saa_plan_create")
         self.h = h
+        self._set_halo_and_finalize(halo)
+        del self._indptr, self._indices, self._data
+
+    @classmethod
+    def from_device(cls, n_dof, indptr_ptr, indices_ptr, data_ptr, F_ptr, lM_ptr, Local_Dirichlet, dt, alpha, device=0,
+                    halo=None, rank=0, size=1):
+        """Plan from a CSR that already lives on the GPU (raw device pointers; int64 indptr, int32 indices)."""
+        self = cls.__new__(cls)
+        D = np.ascontiguousarray(Local_Dirichlet, dtype=np.int64).reshape(-1)
+        self.n_dof, self.rank, self.size, self.device = int(n_dof), int(rank), int(size), int(device)
+        self.dt, self.dt2, self.dt_half, self.half_alpha, self.alpha = step_scalars(dt, alpha)
+        h = ctypes.c_void_p()
+        _check(lib().saa_plan_create_dev(ctypes.byref(h), device, int(n_dof), indptr_ptr, indices_ptr, data_ptr, F_ptr, lM_ptr,
+                                         _p(D), D.size, self.dt, self.dt2, self.dt_half, self.half_alpha, self.alpha),
+               "saa_plan_create_dev")
+        self.h = h
+        self._set_halo_and_finalize(halo)
+        return self
+
+    def _set_halo_and_finalize(self, halo):
+        L, h, rank, size = lib(), self.h, self.rank, self.size
         if size > 1:
             if halo is None:
                 raise SaaError("size > 1 needs the halo description (maps.halo_plan)")
@@ -164,7 +190,6 @@ class StepPlan:
             _check(L.saa_plan_set_halo(h, rank, size, sp.size, _p(sp), nb.size, _p(nb), _p(ptr), _p(send), _p(hp),
                                        _p(hr), _p(hs)), "saa_plan_set_halo")
         _check(L.saa_plan_finalize(h), "saa_plan_finalize")
-        del self._indptr, self._indices, self._data
 
     # ---- facts -------------------------------------------------------------------------------------
     @property
