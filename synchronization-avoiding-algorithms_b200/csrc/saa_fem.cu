@@ -434,6 +434,7 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     // host copies are no longer needed
     std::vector<int32_t>().swap(p->indptr); std::vector<int32_t>().swap(p->indices);
     std::vector<double>().swap(p->data); std::vector<double>().swap(p->F); std::vector<double>().swap(p->M);
+    CK(cudaDeviceSynchronize());   // set-up work ran on the default stream; the plan's stream is non-blocking
     p->finalized = true;
     return 0;
 }
