@@ -34,7 +34,10 @@ def test_device_assembly_matches_host_assembly(m, size, rank):
     assert (np.abs(diff.data).max() if diff.nnz else 0.0) <= 4e-15 * scale      # entries: a few ulp of the block scale
     assert Kd.has_sorted_indices and np.all(np.diff(Kd.indptr) > 0)
     assert np.all(Kd.data != 0)                                                  # exact zeros dropped (:150)
-    assert abs(Kd.nnz - Kh.nnz) <= 0.02 * Kh.nnz                                 # which entries cancel to 0.0 may differ
+    # the closed form yields exact zeros where the reference's BLAS evaluation leaves ~1e-16-relative residues
+    # (stored by csr_matrix): the device pattern is a subset; the dropped entries are covered by the bound above
+    assert Kd.nnz <= Kh.nnz and (Kh.nnz - Kd.nnz) <= 0.2 * Kh.nnz
+    assert ((Kd != 0).astype(np.int8) - (Kd != 0).multiply(Kh != 0).astype(np.int8)).nnz == 0
     # partial lumped mass / load of the local elements, dt, clamped DOFs
     lMh, Fh = assembly.lumped_mass_and_load(pts, cells[ele], 1, 0.5)
     dof = maps.node_to_dof(3, [0, 1, 2], nodes)
