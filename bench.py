@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — DOF-steps/s of the explicit FE time step on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--m M] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--refine M] [--impl native|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is ONE explicit time step (one pass of Dynamic_solver.py:9-34 over the whole mesh): force K.u,
@@ -9,7 +9,7 @@ central-difference update, Dirichlet clamp and — for N > 1 — the shared-node
 Workload (config.workload): the 25 x 1 x 1 cantilever of Mesh_info/beam_US.geo as a structured tet mesh with
 m cells per unit length.  Defaults follow BASELINE.json's configs: one GPU -> m = 24 (1.13 M DOF, "~1M DOF,
 single B200, fp64"); N > 1 -> m = 65 (21.2 M DOF, "~20M DOF over 2/4/8 B200") cut into N x-slabs, one
-process per GPU, shared-node forces exchanged every step.  --m 111 is the 104 M-DOF mesh of the 100M sweep.
+process per GPU, shared-node forces exchanged every step.  --refine 111 is the 104 M-DOF mesh of the 100M sweep.
 
 `value`   whole-job DOF-steps/s with the state resident in HBM (CUDA events on the plan's stream, max over ranks).
 `e2e`     the same metric through the reference-facing call saa_step_host — one parallel_explicit_solver_dis_pre
@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=0, help="timed time steps (0: 10000 for m <= 32, else 2000)")
     ap.add_argument("--warmup", type=int, default=100)
-    ap.add_argument("--m", type=int, default=0, help="cells per unit length of the 25x1x1 beam (0: default for N)")
+    ap.add_argument("--refine", "--m", dest="m", type=int, default=0,
+                    help="cells per unit length of the 25x1x1 beam (0: default for N); spell it --refine under torchrun")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed host-call steps (0: 200 for m <= 32, else 30)")
     ap.add_argument("--launch", default="auto", choices=["auto", "per_step", "graph", "persistent"])

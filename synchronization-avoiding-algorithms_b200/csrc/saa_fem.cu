@@ -123,7 +123,9 @@ struct saa_plan {
     // halo device
     double *d_xbuf = nullptr, *d_send = nullptr;
     double *d_recv = nullptr;               // peer region: [2 parities x total_msg doubles | n_nb arrival flags (u64)]
-    unsigned int *d_done = nullptr;
+    unsigned int *d_done = nullptr;          // [0] boundary completion counter, [1] error word
+    unsigned long long *d_own_ready = nullptr;
+    bool peer_fused = true;                 // one fused launch per synchronised step (SAA_PEER_FUSED=0: three kernels)
     int32_t *d_dst_nb = nullptr;
     // peer-memory transport
     bool peer = false;
@@ -413,15 +415,17 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
         const size_t region = (size_t)(2 * p->total_msg) * sizeof(double) + (size_t)std::max(n_nb, 1) * sizeof(unsigned long long);
         CK(cudaMalloc((void **)&p->d_recv, region));
         CK(cudaMemset(p->d_recv, 0, region));
-        CK(cudaMalloc((void **)&p->d_done, sizeof(unsigned int)));
-        CK(cudaMemset(p->d_done, 0, sizeof(unsigned int)));
+        CK(cudaMalloc((void **)&p->d_done, 2 * sizeof(unsigned int)));
+        CK(cudaMemset(p->d_done, 0, 2 * sizeof(unsigned int)));
+        CK(cudaMalloc((void **)&p->d_own_ready, sizeof(unsigned long long)));
+        CK(cudaMemset(p->d_own_ready, 0, sizeof(unsigned long long)));
         if (upload(&p->d_dst_nb, dst_nb)) return -1;
         CK(cudaMalloc((void **)&p->d_send, std::max<int64_t>(p->total_msg, 1) * sizeof(double)));
         p->H.sh_rows = sh_pad; p->H.xbuf = p->d_xbuf; p->H.sendbuf = p->d_send;
         p->H.recv = p->d_recv; p->H.recv_stride = p->total_msg;
         p->H.dst_ptr = p->d_dst_ptr; p->H.dst_pos = p->d_dst_pos; p->H.dst_nb = p->d_dst_nb;
         p->H.src_ptr = p->d_src_ptr; p->H.src_pos = p->d_src_pos;
-        p->H.n_nb = n_nb; p->H.done_ctr = p->d_done;
+        p->H.n_nb = n_nb; p->H.done_ctr = p->d_done; p->H.err = p->d_done + 1; p->H.own_ready = p->d_own_ready;
         p->H.flags = (const unsigned long long *)(p->d_recv + 2 * p->total_msg);
     }
 
@@ -452,7 +456,7 @@ extern "C" int saa_plan_destroy(saa_plan *p)
         for (void *m : p->peer_mapped) cudaIpcCloseMemHandle(m);
         void *ptrs[] = {p->d_slice_ptr, p->d_val, p->d_col, p->d_M, p->d_F, p->d_dir, p->d_iperm, p->d_buf[0], p->d_buf[1],
                         p->d_clk, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
-                        p->d_recv, p->d_done, p->d_dst_nb, p->d_dst_pos_peer, p->d_peer_recv, p->d_peer_stride, p->d_peer_flag,
+                        p->d_recv, p->d_done, p->d_own_ready, p->d_dst_nb, p->d_dst_pos_peer, p->d_peer_recv, p->d_peer_stride, p->d_peer_flag,
                         p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force};
         for (void *q : ptrs)
             if (q) cudaFree(q);
@@ -758,6 +762,15 @@ static int step_sync_nccl(saa_plan *p, int64_t n_steps)
 // peer transport: three stream-ordered kernels per step, no host involvement -> replayed from a two-step graph
 static void launch_peer_step(saa_plan *p, cudaStream_t st)
 {
+    if (p->peer_fused && p->sh_slices > 0) {
+        const unsigned n_main = nblk(p->n_slices, SAA_WARPS_PER_BLOCK);
+        const unsigned n_tail = nblk(p->H.sh_rows, 256);
+        saa_k_step_fused<<<n_main + n_tail, 256, 0, st>>>(p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
+                                                         p->d_clk + (p->cur ^ 1), n_main);
+        p->launches++;
+        p->cur ^= 1;
+        return;
+    }
     sync_phase_boundary(p, st);
     sync_phase_interior(p, st);
     sync_phase_shared(p, st);
@@ -781,7 +794,7 @@ static int step_sync_peer(saa_plan *p, int64_t n_steps, int launch)
             CK(cudaGraphInstantiate(&p->graph_peer[c], g, 0));
             CK(cudaGraphDestroy(g));
         }
-        const int per = (p->sh_slices > 0 ? 3 : 1) * 2;
+        const int per = (p->sh_slices > 0 ? (p->peer_fused ? 1 : 3) : 1) * 2;
         for (; done + 2 <= n_steps; done += 2) {
             CK(cudaGraphLaunch(p->graph_peer[c], st));
             p->launches += per;
@@ -818,6 +831,11 @@ extern "C" int saa_plan_synchronize(saa_plan *p)
     NEED_FINAL(p, "saa_plan_synchronize");
     CK(cudaSetDevice(p->device));
     CK(cudaStreamSynchronize(p->stream));
+    if (p->peer && p->d_done) {
+        unsigned int err = 0;
+        CK(cudaMemcpy(&err, p->d_done + 1, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) return fail("saa_plan_synchronize: a wait for a neighbour's halo message expired (ranks out of step?)");
+    }
     return 0;
 }
 
@@ -1034,7 +1052,7 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
     NEED_FINAL(p, "saa_plan_peer_attach");
     if (n_nb != (int)p->nb_rank.size()) return fail("saa_plan_peer_attach: %d handles for %d neighbours", n_nb, (int)p->nb_rank.size());
     if (p->peer) return fail("saa_plan_peer_attach: already attached");
-    if (n_nb > 256) return fail("saa_plan_peer_attach: more than 256 neighbours");
+    if (n_nb > 255) return fail("saa_plan_peer_attach: more than 255 neighbours");
     if (n_nb == 0) { p->peer = true; p->Hp = p->H; return 0; }
     if (!handles64 || !remote_off || !remote_total || !remote_slot || !remote_n_nb) return fail("saa_plan_peer_attach: null argument");
     CK(cudaSetDevice(p->device));
@@ -1064,6 +1082,8 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
     p->Hp = p->H;
     p->Hp.dst_pos = p->d_dst_pos_peer;
     p->Hp.peer_recv = p->d_peer_recv; p->Hp.peer_stride = p->d_peer_stride; p->Hp.peer_flag = p->d_peer_flag;
+    const char *fz = getenv("SAA_PEER_FUSED");
+    p->peer_fused = !(fz && fz[0] == '0');
     p->peer = true;
     return 0;
 }

@@ -62,6 +62,8 @@ struct SaaHaloDev {
     unsigned long long *const *peer_flag;   // [n_nb] the neighbour's arrival flag for messages from this rank
     const unsigned long long *flags;        // [n_nb] local arrival flags, flag[k] = number of messages received from k
     unsigned int *done_ctr;                 // blocks of the pack kernel that have finished (last one raises the flags)
+    unsigned long long *own_ready;          // fused step: number of steps whose own boundary forces are complete
+    unsigned int *err;                      // set when a bounded wait expired (a peer never delivered)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
@@ -74,6 +76,27 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bounded spin (about two seconds): a peer that never delivers must not hang the GPU
+template <bool SYS>
+__device__ __forceinline__ void saa_wait_ge(const unsigned long long *flag, unsigned long long target, unsigned int *err)
+{
+    const long long t0 = clock64();
+    while ((SYS ? ld_acquire_sys_u64(flag) : ld_acquire_gpu_u64(flag)) < target) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1ll << 32)) { *err = 1u; break; }
+    }
+}
+
 
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(256) saa_k_shared_update(SaaDev P, SaaHaloDev 
     if (PEER) {
         const unsigned long long step = clk_in->sync_step;
         if (threadIdx.x < H.n_nb) {
-            while (ld_acquire_sys_u64(H.flags + threadIdx.x) < step + 1ull) __nanosleep(64);
+            saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
         }
         __syncthreads();
         recv += (int64_t)(step & 1ull) * H.recv_stride;
@@ -267,6 +290,70 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
         Fi = __dadd_rn(Fi, f[row]);
     }
     out[row] = Fi;
+}
+
+// K1+K2+K3 in ONE launch per synchronised step (peer transport).  Blocks are dispatched in index order, so
+//   * the first blocks own the boundary slices (internal order is boundary-first): partial forces -> own buffer
+//     and straight into the neighbours' receive areas; the warp that completes the last boundary slice raises
+//     the neighbours' arrival flags (system scope) and the local "own forces ready" flag;
+//   * the bulk of the grid streams the interior slices exactly like saa_k_step<true>, overlapping the NVLink
+//     traffic;
+//   * the last few blocks (index >= n_main) wait for the arrival flags, then do the rank-ordered sum and the
+//     update of the shared rows.
+// Same arithmetic, same order as the three-kernel sequence — one launch gap and no pipeline drain per step.
+__global__ void __launch_bounds__(256) saa_k_step_fused(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
+                                                        double *__restrict__ dn_d1, const SaaClock *clk_in, SaaClock *clk_out,
+                                                        unsigned int n_main)
+{
+    const unsigned long long step = clk_in->sync_step;
+    const double tn = clk_in->tn;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        clk_out->tn = __dadd_rn(tn, P.dt);
+        clk_out->sync_step = step + 1ull;
+    }
+    if (blockIdx.x < n_main) {
+        const int lane = threadIdx.x & 31;
+        const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (slice >= P.n_slices) return;
+        double s = saa_row_dot<8, true>(P, slice, lane, d0);
+        if (slice < P.sh_slices) {
+            const int64_t row = slice * 32 + lane;
+            H.xbuf[row] = s;
+            for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+                const int nb = H.dst_nb[k];
+                H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s;
+            }
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int t = atomicAdd(H.done_ctr, 1u);
+                if (t == (unsigned int)P.sh_slices - 1u) {
+                    *H.done_ctr = 0u;
+                    __threadfence_system();
+                    for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
+                    st_release_gpu_u64(H.own_ready, step + 1ull);
+                }
+            }
+        } else {
+            s = __dadd_rn(0.0, s);
+            saa_finish_row(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
+        }
+        return;
+    }
+    // tail blocks: shared rows
+    if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
+    if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
+    __syncthreads();
+    const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
+    const int64_t row = (int64_t)(blockIdx.x - n_main) * blockDim.x + threadIdx.x;
+    if (row >= H.sh_rows) return;
+    double Fi = 0.0;
+    for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+        const int32_t q = H.src_pos[k];
+        const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
+        Fi = __dadd_rn(Fi, v);
+    }
+    saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(tn));
 }
 
 // Persistent variant of K1 (local mode): one cooperative launch runs n_steps time steps; u stays in HBM/L2,
