@@ -178,7 +178,7 @@ def cpu_baseline(csr, n_nodes, dt, seconds):
                        f"{threads} threads); the reference itself is single-threaded numpy/scipy per MPI rank"), k, secs
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the CPU restatement of the reference's own path on the host cores (the reference is
     Python and does not exist on the GPU box; oracle/fem_oracle.c is its pinned, bit-exact port).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -205,7 +205,7 @@ def run_reference(args):
                        "note": f"requested --steps {args.steps or 'default'} bounded to {k} CPU time steps of the full mesh"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "DOF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def time_resident(pl, torch, stream, steps, warmup, mode, launch, barrier):
@@ -224,8 +224,18 @@ def time_resident(pl, torch, stream, steps, warmup, mode, launch, barrier):
 
 def main():
     args = parse()
+    # keep stdout clean for the single JSON line: libraries (NCCL's version banner, torchrun notices) write to it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
     import torch
     import torch.distributed as dist
@@ -358,7 +368,7 @@ def main():
                 nn, dt24 = info["n_nodes"], dtv
             cb, _, _ = cpu_baseline(csr, nn, dt24, args.cpu_seconds)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
