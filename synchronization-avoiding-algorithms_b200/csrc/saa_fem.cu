@@ -814,6 +814,7 @@ extern "C" int saa_plan_step(saa_plan *p, int64_t n_steps, int mode, int launch)
     NEED_FINAL(p, "saa_plan_step");
     if (n_steps < 0) return fail("saa_plan_step: negative n_steps");
     if (n_steps == 0) return 0;
+    if (p->group) return fail("saa_plan_step: this plan belongs to a group; use saa_group_step");
     CK(cudaSetDevice(p->device));
     if (mode == SAA_MODE_LOCAL || mode == SAA_MODE_PREDICT) return step_local(p, n_steps, mode, launch);
     if (mode == SAA_MODE_SYNC) {
@@ -830,7 +831,7 @@ extern "C" int saa_plan_synchronize(saa_plan *p)
 {
     NEED_FINAL(p, "saa_plan_synchronize");
     CK(cudaSetDevice(p->device));
-    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaStreamSynchronize(plan_stream(p)));
     if (p->peer && p->d_done) {
         unsigned int err = 0;
         CK(cudaMemcpy(&err, p->d_done + 1, sizeof err, cudaMemcpyDeviceToHost));

@@ -1,0 +1,138 @@
+"""The LSTM refill predictor (Tools/DNN_tools.py, Tools/DNN_prediction.py) against golden vectors recorded from the
+unmodified reference (oracle/gen_golden_lstm.py), and the device sync-avoiding loop against a CPU emulation of
+Online_predictor.py:251-318 built on the oracle.
+
+Tolerance: the reference runs the n_s combs one by one (batch 1, CPU); here they are one batch (and on the GPU
+tests cuDNN kernels), so agreement is to float32 rounding: |diff| <= 2e-5 * (scale_max - scale_min), the value
+SURVEY.md §8 a11 measured as ~6e-8 relative in the scaled space, amplified by the 20-step recursion."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, ROOT, bits_equal, load_golden, oracle_module
+
+PKG = os.path.join(ROOT, "synchronization-avoiding-algorithms_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+
+def _load(name):
+    import torch
+    from Tools.DNN_tools import LSTM_encoder_decoder
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    model = LSTM_encoder_decoder(int(z["input_size"]), int(z["hidden_size"]), 2, True, 0.0, 0.0)
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}
+    assert set(sd) == set(model.state_dict())             # the reference's checkpoint keys load unchanged
+    model.load_state_dict(sd)
+    return z, model
+
+
+@pytest.mark.parametrize("name", ["lstm_small", "lstm_wide", "lstm_short"])
+def test_predictor_matches_reference_cpu(name):
+    from Tools.DNN_prediction import comb_indices, encoder_decoder_predictor, predict_block
+    import torch
+    z, model = _load(name)
+    n, n_p, n_f, n_s = int(z["n"]), int(z["n_p"]), int(z["n_f"]), int(z["n_s"])
+    smax, smin = float(z["scale_max"]), float(z["scale_min"])
+    NF = encoder_decoder_predictor("cpu", n, model, n_p, n_f, n_s, int(z["input_size"]), z["d_sol"], smax, smin)
+    assert NF.shape == z["NF"].shape
+    assert np.abs(NF - z["NF"]).max() <= 2e-5 * (smax - smin)
+    # the block form used by the device loop gives the same table
+    hist = torch.from_numpy(z["d_sol"][n - n_p * n_s:n])
+    T = predict_block(model, hist, n_p, n_f, n_s, smax, smin).numpy()
+    assert np.abs(T - z["NF"]).max() <= 2e-5 * (smax - smin)
+    past, fut = comb_indices(n, n_p, n_f, n_s)
+    assert past.shape == (n_s, n_p) and fut.shape == (n_s, n_f) and past.max() == n - 1 and fut.min() == n
+
+
+def test_scaling_and_windows_follow_the_reference_formulas():
+    import torch
+    from Tools.DNN_tools import Scale_to_zero_one, scale_forward, scale_it_back, windows_from_history
+    rng = np.random.default_rng(0)
+    H = rng.standard_normal((400, 6))
+    X, Y = windows_from_history(H, 6, 5, 4, 3, 0.5)
+    sub = H[:200][::5]
+    assert X.shape == (40 - 3 - 4 + 1, 4, 6) and Y.shape == (34, 3, 6)
+    for i in (0, 7, 33):
+        assert np.array_equal(X[i].numpy(), sub[i:i + 4].astype(np.float32)) and np.array_equal(Y[i].numpy(), sub[i + 4:i + 7].astype(np.float32))
+    Xs, Ys, mx, mn = Scale_to_zero_one(X, Y)
+    assert float(Xs.max()) <= 0 and float(min(Xs.min(), Ys.min())) == -1.0
+    a = torch.from_numpy(H)
+    assert torch.allclose(scale_it_back(scale_forward(a, 2.0, -3.0), 2.0, -3.0), a, atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lstm_small", "lstm_wide"])
+def test_predictor_matches_reference_on_gpu(name):
+    import torch
+    from Tools.DNN_prediction import predict_block
+    z, model = _load(name)
+    n, n_p, n_f, n_s = int(z["n"]), int(z["n_p"]), int(z["n_f"]), int(z["n_s"])
+    smax, smin = float(z["scale_max"]), float(z["scale_min"])
+    hist = torch.from_numpy(z["d_sol"][n - n_p * n_s:n]).cuda()
+    T = predict_block(model.cuda(), hist, n_p, n_f, n_s, smax, smin).cpu().numpy()
+    assert np.abs(T - z["NF"]).max() <= 5e-5 * (smax - smin)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resync", [None, 4])
+def test_sync_avoiding_loop_equals_cpu_emulation(resync):
+    """beam_coarse, 2 partitions on one GPU: warm-up synchronised, then refill blocks with on-device LSTM tables.
+    The FE arithmetic must equal the oracle emulation of Online_predictor.py:251-318 BITWISE when the emulation
+    is fed the very same tables."""
+    import scipy.sparse as sp
+    import torch
+    import saa_b200  # noqa: F401
+    from saa_b200 import maps, plan as splan, sync_avoiding
+    from Tools.DNN_tools import LSTM_encoder_decoder
+    g = load_golden("beam_coarse_P2")
+    P = 2
+    lists = [r["nodes"] for r in g["ranks"]]
+    plans = []
+    for q, r in enumerate(g["ranks"]):
+        n = r["F"].size
+        K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+        plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), halo=maps.halo_plan(q, P, lists), rank=q, size=P))
+    grp = splan.PlanGroup(plans)
+    n_p, n_f, n_s = 4, 3, 5
+    dofs = [r["loc_dof_shared"] for r in g["ranks"]]
+    torch.manual_seed(7)
+    models = [LSTM_encoder_decoder(d.size, 8, 2, True, 0.0, 0.0) for d in dofs]
+    scales = [(1e-4, -3e-4), (2e-4, -2e-4)]
+    run = sync_avoiding.SyncAvoidingRun(plans, grp, dofs, models, scales, n_p, n_f, n_s, resync_every=resync, keep_tables=True)
+    test_num = n_p * n_s + 2 * n_f * n_s + 4                 # two full refill blocks and a partial one
+    run.run(test_num)
+    grp.synchronize()
+    # --- CPU emulation with the oracle, same tables
+    o = oracle_module().OracleProblem(len(g["points"]), g["ranks"], g["dt"], float(g["alpha"]))
+    hist = [np.zeros((test_num, d.size)) for d in dofs]
+    i = 0
+    for _ in range(n_p * n_s):                               # :253-275
+        o.run(1)
+        for q in range(P):
+            hist[q][i] = o.d0(q)[dofs[q]]
+        i += 1
+    blk = 0
+    while i < test_num:
+        tabs = run.tables[blk]
+        for k in range(min(n_f * n_s, test_num - i)):        # :284-316
+            if resync and i % resync == 0:
+                o.run(1)
+            else:
+                o.run(1, model=True)
+                for q in range(P):
+                    d0, dn, tn = o.state(q)
+                    d0[dofs[q]] = tabs[q][k]                 # :298
+                    o.set_state(q, d0, dn, tn)
+            for q in range(P):
+                hist[q][i] = o.d0(q)[dofs[q]]
+            i += 1
+        blk += 1
+    for q in range(P):
+        assert bits_equal(plans[q].d0(), o.d0(q)), q
+        cap = n_p * n_s + n_f * n_s
+        H = plans[q].read_history(test_num - cap, cap)
+        assert bits_equal(H, hist[q][test_num - cap:]), q
+    assert len(run.tables) == 3
