@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="N = 1: skip the extra 21 M-DOF measurement")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo transport for N > 1")
+    ap.add_argument("--sync-avoid", default="", help="N > 1: also time the synchronization-avoiding loop (BASELINE config 5); "
+                    "comma list of re-sync periods k, 0 = never re-synchronise (the reference's behaviour), e.g. 0,10,50")
+    ap.add_argument("--filter-size", type=int, default=150, help="n_s of the LSTM refill (Online_predictor.py:57)")
     return ap.parse_args()
 
 
@@ -222,6 +225,47 @@ def time_resident(pl, torch, stream, steps, warmup, mode, launch, barrier):
     return e0.elapsed_time(e1), pl.kernel_launches - l0
 
 
+def time_sync_avoiding(pl, args, torch, stream, barrier, max_over_ranks, n_dof_global, local):
+    """BASELINE config 5: the loop of Online_predictor.py:251-318 on the device — LSTM encoder-decoder (the reference's
+    architecture: 2-layer bidirectional encoder, hidden 50, n_past = n_future = 20; random-init weights, synthetic)
+    predicts this rank's shared-DOF displacements on the GPU, un-synchronised steps overwrite them; a true
+    exchange runs every k steps (k = 0: never again after the warm-up, the reference's behaviour)."""
+    from saa_b200 import sync_avoiding
+    sys.path.insert(0, os.path.join(ROOT, "synchronization-avoiding-algorithms_b200"))
+    from Tools.DNN_tools import LSTM_encoder_decoder
+    nb, off = pl.halo_layout()
+    hp = pl._halo_desc
+    dofs = (3 * np.asarray(hp["shared_pos"], dtype=np.int64)[:, None] + np.arange(3)[None, :]).ravel()
+    n_p = n_f = 20
+    n_s = args.filter_size
+    out = {"n_past": n_p, "n_future": n_f, "filter_size": n_s, "input_size_rank0": int(dofs.size), "hidden": 50,
+           "model": "LSTM_encoder_decoder(input, 50, 2, bidirectional) random-init, fp32, on-device (PyTorch/cuDNN)", "runs": []}
+    torch.manual_seed(1234 + pl.rank)
+    model = LSTM_encoder_decoder(int(dofs.size), 50, 2, True, 0.0, 0.0)
+    for k in [int(x) for x in args.sync_avoid.split(",")]:
+        d0, dn, tn = pl.get_state()
+        run = sync_avoiding.SyncAvoidingRun([pl], pl, [dofs], [model], [(1e-3, -1e-2)], n_p, n_f, n_s, device=f"cuda:{local}",
+                                            resync_every=(k or None))
+        # the history ring starts at this call: warm-up = n_p*n_s synchronised steps, then whole refill blocks are timed
+        run.i = 0
+        base = pl.history_count
+        run.run(n_p * n_s)
+        pl.synchronize()
+        barrier()
+        blocks = max(1, min(3, 6000 // (n_f * n_s)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        run.run(n_p * n_s + blocks * n_f * n_s)
+        pl.synchronize()
+        barrier()
+        ms = max_over_ranks((time.perf_counter() - w0) * 1e3)         # wall clock: includes the LSTM inference of every block
+        nst = blocks * n_f * n_s
+        out["runs"].append({"resync_every": k, "steps": nst, "ms_per_step": ms / nst, "value": n_dof_global * nst / (ms * 1e-3),
+                            "unit": "DOF-steps/s"})
+        pl.set_history(None, 0, 1)
+    return out
+
+
 def main():
     args = parse()
     # keep stdout clean for the single JSON line: libraries (NCCL's version banner, torchrun notices) write to it
@@ -335,6 +379,10 @@ def main():
         except Exception as e:
             also = {"error": str(e)[:200]}
 
+    sync_avoid = None
+    if world > 1 and args.sync_avoid:
+        sync_avoid = time_sync_avoiding(pl, args, torch, stream, barrier, max_over_ranks, n_dof_global, local)
+
     if rank == 0:
         line = {
             "metric": "DOF-steps/sec", "value": n_dof_global * steps / (ms * 1e-3), "unit": "DOF-steps/s",
@@ -359,6 +407,8 @@ def main():
         }
         if also is not None:
             line["also"] = also
+        if sync_avoid is not None:
+            line["sync_avoiding"] = sync_avoid
         if want_cpu:
             csr = info["csr"]
             if csr is None:     # large mesh: time the CPU on the 1.13 M-DOF mesh instead (DOF-normalised metric)

@@ -174,6 +174,7 @@ class StepPlan:
 
     def _set_halo_and_finalize(self, halo):
         L, h, rank, size = lib(), self.h, self.rank, self.size
+        self._halo_desc = halo
         if size > 1:
             if halo is None:
                 raise SaaError("size > 1 needs the halo description (maps.halo_plan)")
