@@ -14,8 +14,9 @@ process per GPU, shared-node forces exchanged every step.  --refine 111 is the 1
 `value`   whole-job DOF-steps/s with the state resident in HBM (CUDA events on the plan's stream, max over ranks).
 `e2e`     the same metric through the reference-facing call saa_step_host — one parallel_explicit_solver_dis_pre
           evaluation per call with (d0, dn) in pinned HOST memory and d1 returned to HOST memory every step.
-`roofline` algorithmic bytes of the fused force+update kernel (12 B per stored entry + 4 B per
-          row pointer + five fp64 vector streams) / average step time, vs the measured HBM copy bandwidth.
+`roofline` algorithmic bytes of the fused force+update kernel in the format it streams (76 B per stored 3x3 node
+          block + five fp64 vector streams; the scalar-CSR figure of SURVEY.md §8d is reported beside it) / average
+          step time, vs the measured HBM copy bandwidth.
 `cpu_baseline` the CPU oracle (oracle/fem_oracle.c, OpenMP) on the same problem on the box's host cores.
 """
 import argparse
@@ -351,8 +352,13 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---- roofline of the fused force+update kernel (largest shard bounds the step) ------------------
+    # algorithmic bytes of the format actually streamed (node-block sliced ELL): 76 B per stored 3x3 block (nine
+    # fp64 values + one int32 column-node id) + slice offsets + Dirichlet mask words + five fp64 vector streams.
+    # The scalar-CSR figure of SURVEY.md §8d (12 B per stored entry + 4 B per row pointer + 40 B per row) is given
+    # beside it as csr_equivalent.
     nnz = pl.nnz
-    alg_bytes = max_over_ranks(float(nnz * 12 + (n_dof_local + 1) * 4 + 5 * 8 * n_dof_local))
+    alg_bytes = max_over_ranks(float(pl.matrix_bytes + 5 * 8 * n_dof_local))
+    csr_bytes = max_over_ranks(float(nnz * 12 + (n_dof_local + 1) * 4 + 5 * 8 * n_dof_local))
     step_s = ms * 1e-3 / steps
     peak, peak_src = measured_peak()
     achieved = alg_bytes / step_s / 1e9
@@ -371,7 +377,7 @@ def main():
             pl2, info2 = setup_device(65, 1, 0, local)
             st2 = torch.cuda.ExternalStream(pl2.stream, device=torch.device("cuda", local))
             ms2, _ = time_resident(pl2, torch, st2, 1000, 50, splan.MODE_LOCAL, launch, barrier)
-            b2 = pl2.nnz * 12 + (pl2.n_dof + 1) * 4 + 40 * pl2.n_dof
+            b2 = pl2.matrix_bytes + 40 * pl2.n_dof
             also = {"workload": workload_name(65, 3 * info2["n_nodes"], info2["n_elem"]), "steps": 1000,
                     "value": 3 * info2["n_nodes"] * 1000 / (ms2 * 1e-3), "ms_per_step": ms2 / 1000,
                     "roofline_frac": b2 / (ms2 * 1e-6) / 1e9 / peak, "nnz_per_row": pl2.nnz / pl2.n_dof}
@@ -400,8 +406,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_launch": alg_bytes, "bytes_formula": "12*nnz + 4*(rows+1) + 40*rows (largest shard)",
-                         "stored_bytes_per_launch": pl.matrix_bytes + 40 * n_dof_local,
+                         "bytes_per_launch": alg_bytes, "bytes_formula": "76*blocks + 8*(slices+1) + 4*rows/32 + 40*rows (largest shard)",
+                         "csr_equivalent": {"bytes_per_launch": csr_bytes, "formula": "12*nnz + 4*(rows+1) + 40*rows",
+                                            "achieved": csr_bytes / step_s / 1e9, "frac": csr_bytes / step_s / 1e9 / peak},
+                         "blocks_per_node": (pl.padded_entries / 9) / (n_dof_local / 3),
                          "kernel": "saa_k_step (fused K.u + central-difference update + Dirichlet mask)"},
             "clocks": clocks,
         }

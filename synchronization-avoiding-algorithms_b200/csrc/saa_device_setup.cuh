@@ -28,44 +28,72 @@ struct DevBuf {   // RAII scratch
     template <class T> T *as() { return (T *)p; }
 };
 
-// ---- kernels of the device finalize --------------------------------------------------------------------------
-__global__ void saa_k_fin_len(int64_t n, const int64_t *__restrict__ indptr, int32_t *__restrict__ len)
+// ---- kernels of the device finalize (node-block sliced ELL, same layout as the host path) ---------------------
+// three-way merge over the (sorted) rows 3e, 3e+1, 3e+2 of node e: visits the distinct column nodes ascending
+struct SaaRowTriple {
+    int64_t q[3], qe[3];
+    __device__ SaaRowTriple(const int64_t *indptr, int64_t e)
+    {
+        for (int A = 0; A < 3; ++A) { q[A] = indptr[3 * e + A]; qe[A] = indptr[3 * e + A + 1]; }
+    }
+    __device__ int32_t next_col_node(const int32_t *indices) const
+    {
+        int32_t cn = INT32_MAX;
+        for (int A = 0; A < 3; ++A)
+            if (q[A] < qe[A]) cn = min(cn, indices[q[A]] / 3);
+        return cn;
+    }
+};
+__global__ void saa_k_fin_nblk(int64_t n_nodes, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, int32_t *__restrict__ nblk)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_nodes) return;
+    SaaRowTriple t(indptr, e);
+    int32_t cnt = 0;
+    for (;;) {
+        const int32_t cn = t.next_col_node(indices);
+        if (cn == INT32_MAX) break;
+        for (int A = 0; A < 3; ++A)
+            while (t.q[A] < t.qe[A] && indices[t.q[A]] / 3 == cn) ++t.q[A];
+        ++cnt;
+    }
+    nblk[e] = cnt;
+}
+__global__ void saa_k_fin_flag(int64_t m, const int32_t *__restrict__ nodes, uint8_t *__restrict__ flag)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) len[i] = (int32_t)(indptr[i + 1] - indptr[i]);
+    if (i < m) flag[nodes[i]] = 1;
 }
-__global__ void saa_k_fin_flag(int64_t m, const int32_t *__restrict__ rows, uint8_t *__restrict__ flag)
+// key of the sigma sort: (window of SIGMA consecutive positions, decreasing block count)
+__global__ void saa_k_fin_keys(int64_t m, const int32_t *__restrict__ nodes, const int32_t *__restrict__ nblk, uint64_t *__restrict__ key)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) flag[rows[i]] = 1;
+    if (i < m) key[i] = ((uint64_t)(i / SAA_SIGMA) << 32) | (uint32_t)(0x7fffffff - nblk[nodes[i]]);
 }
-// key of the sigma sort: (window of SIGMA consecutive positions, decreasing length)
-__global__ void saa_k_fin_keys(int64_t m, const int32_t *__restrict__ rows, const int32_t *__restrict__ len, uint64_t *__restrict__ key)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) key[i] = ((uint64_t)(i / SAA_SIGMA) << 32) | (uint32_t)(0x7fffffff - len[rows[i]]);
-}
-__global__ void saa_k_fin_perm(int64_t m, const int32_t *__restrict__ rows, int64_t offset, int32_t *__restrict__ perm, int32_t *__restrict__ iperm)
+// permn: internal node -> external node; iperm: external row -> internal row
+__global__ void saa_k_fin_perm(int64_t m, const int32_t *__restrict__ nodes, int64_t offset, int32_t *__restrict__ permn, int32_t *__restrict__ iperm)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) {
-        perm[offset + i] = rows[i];
-        iperm[rows[i]] = (int32_t)(offset + i);
+        const int32_t e = nodes[i];
+        permn[offset + i] = e;
+        for (int c = 0; c < 3; ++c) iperm[3 * (int64_t)e + c] = (int32_t)(3 * (offset + i) + c);
     }
 }
-__global__ void saa_k_fin_slice_len(int64_t n_slices, const int32_t *__restrict__ perm, const int32_t *__restrict__ len, int64_t *__restrict__ cnt)
+__global__ void saa_k_fin_slice_len(int64_t n_slices, const int32_t *__restrict__ permn, const int32_t *__restrict__ nblk, int64_t *__restrict__ cnt)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slices) return;
     int32_t mx = 0;
     for (int l = 0; l < 32; ++l) {
-        const int32_t r = perm[s * 32 + l];
-        if (r >= 0) mx = max(mx, len[r]);
+        const int32_t e = permn[s * 32 + l];
+        if (e >= 0) mx = max(mx, nblk[e]);
     }
     cnt[s] = 32 * (int64_t)mx;
 }
-// one warp per slice: copy the rows of the slice into the strided layout (stored order kept), pad with 0.0 * d0[own row]
-__global__ void saa_k_fin_fill(int64_t n_slices, const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ perm,
+// one warp per slice: every lane writes the blocks of its node (stored order of each row kept), then pads with
+// blocks 0.0 * d0[own node]
+__global__ void saa_k_fin_fill(int64_t n_slices, const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ permn,
                                const int32_t *__restrict__ iperm, const int64_t *__restrict__ indptr,
                                const int32_t *__restrict__ indices, const double *__restrict__ data, double *__restrict__ val,
                                int32_t *__restrict__ col)
@@ -75,27 +103,41 @@ __global__ void saa_k_fin_fill(int64_t n_slices, const int64_t *__restrict__ sli
     if (s >= n_slices) return;
     const int64_t beg = slice_ptr[s];
     const int L = (int)((slice_ptr[s + 1] - beg) >> 5);
-    const int64_t irow = s * 32 + lane;
-    const int32_t r = perm[irow];
-    int64_t src = 0;
-    int cnt = 0;
-    if (r >= 0) { src = indptr[r]; cnt = (int)(indptr[r + 1] - src); }
-    for (int j = 0; j < L; ++j) {
-        double v = 0.0;
-        int32_t c = (int32_t)irow;
-        if (j < cnt) { v = data[src + j]; c = iperm[indices[src + j]]; }
-        val[beg + 32 * (int64_t)j + lane] = v;
-        col[beg + 32 * (int64_t)j + lane] = c;
+    double *vs = val + 9 * beg + lane;
+    int32_t *cs = col + beg + lane;
+    const int64_t inode = s * 32 + lane;
+    const int32_t e = permn[inode];
+    int j = 0;
+    if (e >= 0) {
+        SaaRowTriple t(indptr, e);
+        for (;; ++j) {
+            const int32_t cn = t.next_col_node(indices);
+            if (cn == INT32_MAX) break;
+            double a[9];
+            for (int k = 0; k < 9; ++k) a[k] = 0.0;
+            for (int A = 0; A < 3; ++A)
+                while (t.q[A] < t.qe[A] && indices[t.q[A]] / 3 == cn) {
+                    a[3 * A + indices[t.q[A]] % 3] = data[t.q[A]];
+                    ++t.q[A];
+                }
+            for (int k = 0; k < 9; ++k) vs[32 * (9 * (int64_t)j + k)] = a[k];
+            cs[32 * (int64_t)j] = iperm[3 * (int64_t)cn] / 3;
+        }
+    }
+    for (; j < L; ++j) {
+        for (int k = 0; k < 9; ++k) vs[32 * (9 * (int64_t)j + k)] = 0.0;
+        cs[32 * (int64_t)j] = (int32_t)inode;
     }
 }
-__global__ void saa_k_fin_vectors(int64_t n_rows, const int32_t *__restrict__ perm, const double *__restrict__ M_ext,
+__global__ void saa_k_fin_vectors(int64_t n_rows, const int32_t *__restrict__ permn, const double *__restrict__ M_ext,
                                   const double *__restrict__ F_ext, double *__restrict__ M, double *__restrict__ F)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
-    const int32_t r = perm[i];
-    M[i] = (r >= 0) ? M_ext[r] : 1.0;
-    F[i] = (r >= 0) ? F_ext[r] : 0.0;
+    const int32_t e = permn[i / 3];
+    const int64_t r = 3 * (int64_t)e + (i % 3);
+    M[i] = (e >= 0) ? M_ext[r] : 1.0;
+    F[i] = (e >= 0) ? F_ext[r] : 0.0;
 }
 __global__ void saa_k_fin_dirichlet(int64_t m, const int64_t *__restrict__ dofs, const int32_t *__restrict__ iperm, uint32_t *__restrict__ mask)
 {
@@ -136,86 +178,85 @@ extern "C" int saa_plan_create_dev(saa_plan **out, int device, int64_t n_dof, co
 static int finalize_device(saa_plan *p)
 {
     CK(cudaSetDevice(p->device));
-    const int64_t n = p->n_dof;
-    const int64_t n_shared = (int64_t)p->shared_pos.size();
+    const int64_t n = p->n_dof, nn = n / 3;
+    const int64_t n_sh = (int64_t)p->shared_pos.size();
     CK(cudaMemcpy(&p->nnz, p->in_indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost));
     auto pad32 = [](int64_t v) { return (v + 31) / 32 * 32; };
 
-    // 1. row lengths, shared flags, the two regions in their starting order
-    DevBuf b_len, b_flag, b_sh, b_in, b_key;
-    if (b_len.alloc(n * sizeof(int32_t)) || b_flag.alloc(n) || b_in.alloc(n * sizeof(int32_t))) return -1;
-    int32_t *len = b_len.as<int32_t>();
+    // 1. block counts, shared flags, the two regions in their starting order
+    DevBuf b_nblk, b_flag, b_sh, b_in, b_key;
+    if (b_nblk.alloc(nn * sizeof(int32_t)) || b_flag.alloc(nn) || b_in.alloc(nn * sizeof(int32_t))) return -1;
+    int32_t *nblk_d = b_nblk.as<int32_t>();
     uint8_t *flag = b_flag.as<uint8_t>();
-    saa_k_fin_len<<<nblk(n, 256), 256>>>(n, p->in_indptr, len);
-    CK(cudaMemset(flag, 0, n));
-    std::vector<int32_t> sh_rows_h;
-    sh_rows_h.reserve(3 * n_shared);
-    for (int64_t j = 0; j < n_shared; ++j)
-        for (int c = 0; c < 3; ++c) sh_rows_h.push_back((int32_t)(3 * p->shared_pos[j] + c));
+    saa_k_fin_nblk<<<nblk(nn, 128), 128>>>(nn, p->in_indptr, p->in_indices, nblk_d);
+    CK(cudaMemset(flag, 0, nn));
+    std::vector<int32_t> sh_h(p->shared_pos.begin(), p->shared_pos.end());
     {   // duplicates would break the permutation
-        std::vector<int32_t> chk(sh_rows_h);
+        std::vector<int32_t> chk(sh_h);
         std::sort(chk.begin(), chk.end());
         if (std::adjacent_find(chk.begin(), chk.end()) != chk.end()) return fail("saa_plan_finalize: duplicate shared node");
     }
-    const int64_t n_sh = (int64_t)sh_rows_h.size();
     if (b_sh.alloc(std::max<int64_t>(n_sh, 1) * sizeof(int32_t))) return -1;
-    int32_t *sh_rows = b_sh.as<int32_t>();
+    int32_t *sh_nodes = b_sh.as<int32_t>();
     if (n_sh) {
-        CK(cudaMemcpy(sh_rows, sh_rows_h.data(), n_sh * sizeof(int32_t), cudaMemcpyHostToDevice));
-        saa_k_fin_flag<<<nblk(n_sh, 256), 256>>>(n_sh, sh_rows, flag);
+        CK(cudaMemcpy(sh_nodes, sh_h.data(), n_sh * sizeof(int32_t), cudaMemcpyHostToDevice));
+        saa_k_fin_flag<<<nblk(n_sh, 256), 256>>>(n_sh, sh_nodes, flag);
     }
-    int32_t *in_rows = b_in.as<int32_t>();
-    const int64_t n_in = thrust::copy_if(thrust::device, thrust::counting_iterator<int32_t>(0), thrust::counting_iterator<int32_t>((int32_t)n),
-                                         in_rows, SaaIsZeroFlag{flag}) - in_rows;
-    if (n_in != n - n_sh) return fail("saa_plan_finalize: internal error (interior rows %lld != %lld)", (long long)n_in, (long long)(n - n_sh));
+    int32_t *in_nodes = b_in.as<int32_t>();
+    const int64_t n_in = thrust::copy_if(thrust::device, thrust::counting_iterator<int32_t>(0), thrust::counting_iterator<int32_t>((int32_t)nn),
+                                         in_nodes, SaaIsZeroFlag{flag}) - in_nodes;
+    if (n_in != nn - n_sh) return fail("saa_plan_finalize: internal error (interior nodes %lld != %lld)", (long long)n_in, (long long)(nn - n_sh));
 
     // 2. sigma sort of both regions (stable: ties keep their order, like the host path)
-    if (b_key.alloc(std::max(n_in, n_sh) * sizeof(uint64_t))) return -1;
+    if (b_key.alloc(std::max<int64_t>(std::max(n_in, n_sh), 1) * sizeof(uint64_t))) return -1;
     uint64_t *key = b_key.as<uint64_t>();
     if (n_sh) {
-        saa_k_fin_keys<<<nblk(n_sh, 256), 256>>>(n_sh, sh_rows, len, key);
-        thrust::stable_sort_by_key(thrust::device, key, key + n_sh, sh_rows);
+        saa_k_fin_keys<<<nblk(n_sh, 256), 256>>>(n_sh, sh_nodes, nblk_d, key);
+        thrust::stable_sort_by_key(thrust::device, key, key + n_sh, sh_nodes);
     }
     if (n_in) {
-        saa_k_fin_keys<<<nblk(n_in, 256), 256>>>(n_in, in_rows, len, key);
-        thrust::stable_sort_by_key(thrust::device, key, key + n_in, in_rows);
+        saa_k_fin_keys<<<nblk(n_in, 256), 256>>>(n_in, in_nodes, nblk_d, key);
+        thrust::stable_sort_by_key(thrust::device, key, key + n_in, in_nodes);
     }
     cudaFree(b_key.p); b_key.p = nullptr;
 
-    // 3. permutation (internal -> external, -1 = padding row) and its inverse
-    const int64_t sh_pad = pad32(n_sh), in_pad = pad32(n_in);
-    p->n_rows = sh_pad + in_pad;
-    p->n_slices = p->n_rows / 32;
-    p->sh_slices = sh_pad / 32;
+    // 3. node permutation (internal -> external, -1 = padding) and the row map external -> internal
+    const int64_t sh_padn = pad32(n_sh), in_padn = pad32(n_in);
+    const int64_t n_slots = sh_padn + in_padn;
+    p->n_rows = 3 * n_slots;
+    p->n_slices = n_slots / 32;
+    p->sh_slices = sh_padn / 32;
     if (p->n_rows >= (int64_t)INT32_MAX) return fail("saa_plan_finalize: more than 2^31 rows per partition not supported");
     DevBuf b_perm, b_cnt;
-    if (b_perm.alloc(p->n_rows * sizeof(int32_t))) return -1;
-    int32_t *perm = b_perm.as<int32_t>();
-    CK(cudaMemset(perm, 0xff, p->n_rows * sizeof(int32_t)));
+    if (b_perm.alloc(n_slots * sizeof(int32_t))) return -1;
+    int32_t *permn = b_perm.as<int32_t>();
+    CK(cudaMemset(permn, 0xff, n_slots * sizeof(int32_t)));
     CK(cudaMalloc((void **)&p->d_iperm, n * sizeof(int32_t)));
-    if (n_sh) saa_k_fin_perm<<<nblk(n_sh, 256), 256>>>(n_sh, sh_rows, 0, perm, p->d_iperm);
-    if (n_in) saa_k_fin_perm<<<nblk(n_in, 256), 256>>>(n_in, in_rows, sh_pad, perm, p->d_iperm);
+    if (n_sh) saa_k_fin_perm<<<nblk(n_sh, 256), 256>>>(n_sh, sh_nodes, 0, permn, p->d_iperm);
+    if (n_in) saa_k_fin_perm<<<nblk(n_in, 256), 256>>>(n_in, in_nodes, sh_padn, permn, p->d_iperm);
     cudaFree(b_in.p); b_in.p = nullptr;
 
-    // 4. slice offsets
+    // 4. slice offsets (block-lanes)
     if (b_cnt.alloc((p->n_slices + 1) * sizeof(int64_t))) return -1;
     int64_t *cnt = b_cnt.as<int64_t>();
     CK(cudaMemset(cnt, 0, (p->n_slices + 1) * sizeof(int64_t)));
-    saa_k_fin_slice_len<<<nblk(p->n_slices, 256), 256>>>(p->n_slices, perm, len, cnt);
+    saa_k_fin_slice_len<<<nblk(p->n_slices, 256), 256>>>(p->n_slices, permn, nblk_d, cnt);
     CK(cudaMalloc((void **)&p->d_slice_ptr, (p->n_slices + 1) * sizeof(int64_t)));
     thrust::exclusive_scan(thrust::device, cnt, cnt + p->n_slices + 1, p->d_slice_ptr);
-    CK(cudaMemcpy(&p->padded_entries, p->d_slice_ptr + p->n_slices, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    int64_t lanes = 0;
+    CK(cudaMemcpy(&lanes, p->d_slice_ptr + p->n_slices, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    p->padded_entries = 9 * lanes;
 
-    // 5. matrix in sliced-ELL order, vectors, Dirichlet mask
-    CK(cudaMalloc((void **)&p->d_val, std::max<int64_t>(p->padded_entries, 1) * sizeof(double)));
-    CK(cudaMalloc((void **)&p->d_col, std::max<int64_t>(p->padded_entries, 1) * sizeof(int32_t)));
-    saa_k_fin_fill<<<nblk(p->n_slices, 8), 256>>>(p->n_slices, p->d_slice_ptr, perm, p->d_iperm, p->in_indptr, p->in_indices,
+    // 5. matrix in node-block sliced-ELL order, vectors, Dirichlet mask
+    CK(cudaMalloc((void **)&p->d_val, std::max<int64_t>(9 * lanes, 1) * sizeof(double)));
+    CK(cudaMalloc((void **)&p->d_col, std::max<int64_t>(lanes, 1) * sizeof(int32_t)));
+    saa_k_fin_fill<<<nblk(p->n_slices, 8), 256>>>(p->n_slices, p->d_slice_ptr, permn, p->d_iperm, p->in_indptr, p->in_indices,
                                                   p->in_data, p->d_val, p->d_col);
     CK(cudaMalloc((void **)&p->d_M, p->n_rows * sizeof(double)));
     CK(cudaMalloc((void **)&p->d_F, p->n_rows * sizeof(double)));
-    saa_k_fin_vectors<<<nblk(p->n_rows, 256), 256>>>(p->n_rows, perm, p->in_M, p->in_F, p->d_M, p->d_F);
-    CK(cudaMalloc((void **)&p->d_dir, p->n_slices * sizeof(uint32_t)));
-    CK(cudaMemset(p->d_dir, 0, p->n_slices * sizeof(uint32_t)));
+    saa_k_fin_vectors<<<nblk(p->n_rows, 256), 256>>>(p->n_rows, permn, p->in_M, p->in_F, p->d_M, p->d_F);
+    CK(cudaMalloc((void **)&p->d_dir, (p->n_rows / 32) * sizeof(uint32_t)));
+    CK(cudaMemset(p->d_dir, 0, (p->n_rows / 32) * sizeof(uint32_t)));
     if (!p->dirichlet.empty()) {
         DevBuf b_d;
         if (b_d.alloc(p->dirichlet.size() * sizeof(int64_t))) return -1;
@@ -228,7 +269,7 @@ static int finalize_device(saa_plan *p)
     p->iperm_h.resize(n);
     CK(cudaMemcpy(p->iperm_h.data(), p->d_iperm, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     p->in_indptr = nullptr; p->in_indices = nullptr; p->in_data = nullptr; p->in_F = nullptr; p->in_M = nullptr;
-    return finalize_tail(p, sh_pad);
+    return finalize_tail(p, 3 * sh_padn);
 }
 
 // ---- K6: sparse assembly on the device ---------------------------------------------------------------------------

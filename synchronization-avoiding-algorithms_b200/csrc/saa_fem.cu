@@ -18,7 +18,7 @@
 
 #include "../../include/saa_fem.h"
 
-#define SAA_SIGMA 4096          // rows per sorting window (multiple of 32)
+#define SAA_SIGMA 1024          // nodes per sorting window (multiple of 32)
 #define SAA_WARPS_PER_BLOCK 8
 
 static thread_local std::string g_err;
@@ -248,14 +248,12 @@ static int upload(T **dptr, const std::vector<T> &h)
     return 0;
 }
 
-// order rows of one region: windows of SAA_SIGMA rows sorted by decreasing length (stable)
-static void sigma_sort(std::vector<int64_t> &rows, const std::vector<int32_t> &indptr)
+// order nodes of one region: windows of SAA_SIGMA nodes sorted by decreasing block count (stable)
+static void sigma_sort(std::vector<int64_t> &nodes, const std::vector<int32_t> &nblk)
 {
-    for (size_t w = 0; w < rows.size(); w += SAA_SIGMA) {
-        size_t e = std::min(rows.size(), w + (size_t)SAA_SIGMA);
-        std::stable_sort(rows.begin() + w, rows.begin() + e, [&](int64_t a, int64_t b) {
-            return (indptr[a + 1] - indptr[a]) > (indptr[b + 1] - indptr[b]);
-        });
+    for (size_t w = 0; w < nodes.size(); w += SAA_SIGMA) {
+        size_t e = std::min(nodes.size(), w + (size_t)SAA_SIGMA);
+        std::stable_sort(nodes.begin() + w, nodes.begin() + e, [&](int64_t a, int64_t b) { return nblk[a] > nblk[b]; });
     }
 }
 
@@ -268,73 +266,108 @@ extern "C" int saa_plan_finalize(saa_plan *p)
     if (p->finalized) return 0;
     if (p->dev_input) return finalize_device(p);
     CK(cudaSetDevice(p->device));
-    const int64_t n = p->n_dof;
+    const int64_t n = p->n_dof, nn = n / 3;
     const int64_t n_shared = (int64_t)p->shared_pos.size();
 
-    // 1. internal row order: shared DOFs (canonical interface order), then the rest ascending
-    std::vector<char> is_shared(n, 0);
-    std::vector<int64_t> sh_rows, in_rows;
-    sh_rows.reserve(3 * n_shared);
-    for (int64_t j = 0; j < n_shared; ++j)
-        for (int c = 0; c < 3; ++c) {
-            int64_t r = 3 * p->shared_pos[j] + c;
-            if (is_shared[r]) return fail("saa_plan_finalize: duplicate shared node");
-            is_shared[r] = 1;
-            sh_rows.push_back(r);
+    // 1. block pattern: distinct column nodes of every node (union over its three rows, ascending)
+    std::vector<int64_t> bptr(nn + 1, 0);
+    std::vector<int32_t> bcol;
+    bcol.reserve((size_t)(p->nnz / 6 + nn));
+    std::vector<int32_t> nblk(nn, 0);
+    for (int64_t e = 0; e < nn; ++e) {
+        int32_t q[3] = {p->indptr[3 * e], p->indptr[3 * e + 1], p->indptr[3 * e + 2]};
+        const int32_t qe[3] = {p->indptr[3 * e + 1], p->indptr[3 * e + 2], p->indptr[3 * e + 3]};
+        for (;;) {
+            int32_t cn = INT32_MAX;
+            for (int A = 0; A < 3; ++A)
+                if (q[A] < qe[A]) cn = std::min(cn, p->indices[q[A]] / 3);
+            if (cn == INT32_MAX) break;
+            for (int A = 0; A < 3; ++A)
+                while (q[A] < qe[A] && p->indices[q[A]] / 3 == cn) {
+                    if (q[A] + 1 < qe[A] && p->indices[q[A] + 1] <= p->indices[q[A]])
+                        return fail("saa_plan_finalize: LocalK must have sorted, duplicate-free column indices");
+                    ++q[A];
+                }
+            bcol.push_back(cn);
         }
-    in_rows.reserve(n - sh_rows.size());
-    for (int64_t r = 0; r < n; ++r)
-        if (!is_shared[r]) in_rows.push_back(r);
-    sigma_sort(sh_rows, p->indptr);
-    sigma_sort(in_rows, p->indptr);
-    auto pad32 = [](int64_t v) { return (v + 31) / 32 * 32; };
-    const int64_t sh_pad = pad32((int64_t)sh_rows.size());
-    const int64_t in_pad = pad32((int64_t)in_rows.size());
-    p->n_rows = sh_pad + in_pad;
-    p->n_slices = p->n_rows / 32;
-    p->sh_slices = sh_pad / 32;
-    if (p->n_rows >= (int64_t)INT32_MAX) return fail("saa_plan_finalize: more than 2^31 rows per partition not supported");
-    std::vector<int64_t> perm(p->n_rows, -1);           // internal -> external (-1: padding row)
-    for (size_t i = 0; i < sh_rows.size(); ++i) perm[i] = sh_rows[i];
-    for (size_t i = 0; i < in_rows.size(); ++i) perm[sh_pad + i] = in_rows[i];
-    p->iperm_h.assign(n, -1);
-    for (int64_t i = 0; i < p->n_rows; ++i)
-        if (perm[i] >= 0) p->iperm_h[perm[i]] = (int32_t)i;
+        bptr[e + 1] = (int64_t)bcol.size();
+        nblk[e] = (int32_t)(bptr[e + 1] - bptr[e]);
+    }
 
-    // 2. sliced ELL
+    // 2. internal node order: interface nodes (canonical interface order), then the rest ascending
+    std::vector<char> is_shared(nn, 0);
+    std::vector<int64_t> sh_nodes, in_nodes;
+    sh_nodes.reserve(n_shared);
+    for (int64_t j = 0; j < n_shared; ++j) {
+        const int64_t e = p->shared_pos[j];
+        if (is_shared[e]) return fail("saa_plan_finalize: duplicate shared node");
+        is_shared[e] = 1;
+        sh_nodes.push_back(e);
+    }
+    in_nodes.reserve(nn - sh_nodes.size());
+    for (int64_t e = 0; e < nn; ++e)
+        if (!is_shared[e]) in_nodes.push_back(e);
+    sigma_sort(sh_nodes, nblk);
+    sigma_sort(in_nodes, nblk);
+    auto pad32 = [](int64_t v) { return (v + 31) / 32 * 32; };
+    const int64_t sh_padn = pad32((int64_t)sh_nodes.size());
+    const int64_t in_padn = pad32((int64_t)in_nodes.size());
+    const int64_t n_slots = sh_padn + in_padn;
+    p->n_rows = 3 * n_slots;
+    p->n_slices = n_slots / 32;
+    p->sh_slices = sh_padn / 32;
+    if (p->n_rows >= (int64_t)INT32_MAX) return fail("saa_plan_finalize: more than 2^31 rows per partition not supported");
+    std::vector<int64_t> permn(n_slots, -1);            // internal node -> external node (-1: padding)
+    for (size_t i = 0; i < sh_nodes.size(); ++i) permn[i] = sh_nodes[i];
+    for (size_t i = 0; i < in_nodes.size(); ++i) permn[sh_padn + i] = in_nodes[i];
+    p->iperm_h.assign(n, -1);
+    for (int64_t i = 0; i < n_slots; ++i)
+        if (permn[i] >= 0)
+            for (int c = 0; c < 3; ++c) p->iperm_h[3 * permn[i] + c] = (int32_t)(3 * i + c);
+
+    // 3. node-block sliced ELL
     std::vector<int64_t> slice_ptr(p->n_slices + 1, 0);
     for (int64_t s = 0; s < p->n_slices; ++s) {
         int32_t mx = 0;
         for (int l = 0; l < 32; ++l) {
-            int64_t r = perm[s * 32 + l];
-            if (r >= 0) mx = std::max(mx, p->indptr[r + 1] - p->indptr[r]);
+            const int64_t e = permn[s * 32 + l];
+            if (e >= 0) mx = std::max(mx, nblk[e]);
         }
         slice_ptr[s + 1] = slice_ptr[s] + 32 * (int64_t)mx;
     }
-    p->padded_entries = slice_ptr[p->n_slices];
-    std::vector<double> val(p->padded_entries, 0.0);
-    std::vector<int32_t> col(p->padded_entries);
+    const int64_t lanes = slice_ptr[p->n_slices];
+    p->padded_entries = 9 * lanes;
+    std::vector<double> val((size_t)(9 * lanes), 0.0);
+    std::vector<int32_t> col((size_t)lanes);
     for (int64_t s = 0; s < p->n_slices; ++s) {
-        const int64_t len = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
+        const int64_t L = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
+        double *vs = val.data() + 9 * slice_ptr[s];
+        int32_t *cs = col.data() + slice_ptr[s];
         for (int l = 0; l < 32; ++l) {
-            const int64_t irow = s * 32 + l;
-            const int64_t r = perm[irow];
+            const int64_t inode = s * 32 + l;
+            const int64_t e = permn[inode];
             int64_t cnt = 0;
-            if (r >= 0) {
-                cnt = p->indptr[r + 1] - p->indptr[r];
-                for (int64_t j = 0; j < cnt; ++j) {      // stored order kept: it is the summation order
-                    val[slice_ptr[s] + 32 * j + l] = p->data[p->indptr[r] + j];
-                    col[slice_ptr[s] + 32 * j + l] = p->iperm_h[p->indices[p->indptr[r] + j]];
+            if (e >= 0) {
+                cnt = nblk[e];
+                int32_t q[3] = {p->indptr[3 * e], p->indptr[3 * e + 1], p->indptr[3 * e + 2]};
+                const int32_t qe[3] = {p->indptr[3 * e + 1], p->indptr[3 * e + 2], p->indptr[3 * e + 3]};
+                for (int64_t j = 0; j < cnt; ++j) {
+                    const int32_t cn = bcol[bptr[e] + j];
+                    for (int A = 0; A < 3; ++A)          // stored order kept: entries of a row in ascending column
+                        while (q[A] < qe[A] && p->indices[q[A]] / 3 == cn) {
+                            vs[(9 * j + 3 * A + p->indices[q[A]] % 3) * 32 + l] = p->data[q[A]];
+                            ++q[A];
+                        }
+                    cs[32 * j + l] = p->iperm_h[3 * (int64_t)cn] / 3;
                 }
             }
-            // padding: 0.0 * d0[own row] added at the end of the row leaves the sum unchanged
-            for (int64_t j = cnt; j < len; ++j) col[slice_ptr[s] + 32 * j + l] = (int32_t)irow;
+            // padding blocks: 0.0 * d0[own node] at the end of the rows leaves the sums unchanged
+            for (int64_t j = cnt; j < L; ++j) cs[32 * j + l] = (int32_t)inode;
         }
     }
     std::vector<double> M(p->n_rows, 1.0), F(p->n_rows, 0.0);
-    for (int64_t i = 0; i < p->n_rows; ++i)
-        if (perm[i] >= 0) { M[i] = p->M[perm[i]]; F[i] = p->F[perm[i]]; }
-    std::vector<uint32_t> dir(p->n_slices, 0u);
+    for (int64_t r = 0; r < n; ++r) { M[p->iperm_h[r]] = p->M[r]; F[p->iperm_h[r]] = p->F[r]; }
+    std::vector<uint32_t> dir(p->n_rows / 32, 0u);
     for (int64_t k : p->dirichlet) {
         int32_t i = p->iperm_h[k];
         dir[i >> 5] |= (1u << (i & 31));
@@ -343,6 +376,7 @@ extern "C" int saa_plan_finalize(saa_plan *p)
     if (upload(&p->d_slice_ptr, slice_ptr) || upload(&p->d_val, val) || upload(&p->d_col, col) ||
         upload(&p->d_M, M) || upload(&p->d_F, F) || upload(&p->d_dir, dir) || upload(&p->d_iperm, p->iperm_h))
         return -1;
+    const int64_t sh_pad = 3 * sh_padn;
     return finalize_tail(p, sh_pad);
 }
 
@@ -474,7 +508,8 @@ extern "C" int64_t saa_plan_padded_entries(const saa_plan *p) { return p ? p->pa
 extern "C" int64_t saa_plan_kernel_launches(const saa_plan *p) { return p ? p->launches : -1; }
 extern "C" int64_t saa_plan_matrix_bytes(const saa_plan *p)
 {
-    return p ? p->padded_entries * 12 + (p->n_slices + 1) * 8 + p->n_slices * 4 : -1;
+    // 9 values + one column-node id per stored block, slice offsets, Dirichlet mask words
+    return p ? (p->padded_entries / 9) * 76 + (p->n_slices + 1) * 8 + (p->n_rows / 32) * 4 : -1;
 }
 extern "C" void *saa_plan_stream(saa_plan *p) { return p ? (void *)plan_stream(p) : nullptr; }
 

@@ -10,12 +10,21 @@
 // which nvcc never contracts into FMA, and the row sum runs over the stored entries in order starting
 // from 0.0 — the same sequence of roundings scipy/numpy perform, hence bit-identical results.
 //
-// Storage (HBM): sliced ELL, slice height 32 = one warp.  Entry j of the row handled by lane l of slice
-// s lives at slice_ptr[s] + 32*j + l, so every warp-wide load of values (256 B) and column ids (128 B)
-// is one fully coalesced, 128-byte-aligned request.  Rows are ordered boundary-first (shared DOFs of the
-// partition interface, then interior) and, inside windows of SIGMA rows, by decreasing length, so
-// slices are almost padding-free; all vectors (d0, dn, M, F) live in that internal order and are
-// streamed coalesced.  The only non-streaming access is the gather d0[col].
+// Storage (HBM): node-block sliced ELL.  The stiffness of 3-D elasticity is made of 3x3 node blocks, so one
+// thread owns one NODE (its three DOF rows) and one warp owns a slice of 32 nodes.  Block j of the node of
+// lane l in slice s is stored as nine value planes and one column-node id (slice_ptr counts block-lanes):
+//     value (A,B) of block j :  val[9*slice_ptr[s] + (9*j + 3*A + B)*32 + l]
+//     column node of block j :  col[  slice_ptr[s] + j*32 + l]
+// so every warp-wide load is a fully coalesced, aligned 256-B (values) or 128-B (ids) request, and the column
+// id is shared by the nine entries of a block: 76 B per block instead of 108 B as scalar CSR.  Entries the
+// reference dropped as exact zeros (csr_matrix(dense), Mat_construction.py:150) are stored as 0.0 inside
+// their block; adding 0.0*x leaves a finite row sum bit-identical (the sum starts at +0.0 and can never
+// become -0.0).  Within a row the blocks are in ascending column order and inside a block B = 0,1,2, i.e.
+// exactly the stored order of the CSR row, which is the summation order of csr_matvec.
+// Nodes are ordered boundary-first (nodes of the partition interface, then interior) and, inside windows of
+// SIGMA nodes, by decreasing block count, so slices are almost padding-free; all vectors (d0, dn, M, F) live
+// in that internal order (row = 3*node + component) and are streamed.  The only non-streaming access is the
+// gather of the three d0 components of a column node (24 contiguous bytes).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -23,16 +32,20 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef SAA_UNROLL
+#define SAA_UNROLL 2          // blocks whose loads are in flight together per thread (2 x 76 B x 32 lanes per warp)
+#endif
+
 struct SaaDev {
-    int64_t n_rows;            // padded rows (multiple of 32)
-    int64_t n_slices;          // n_rows / 32
-    int64_t sh_slices;         // slices [0, sh_slices) hold the shared (interface) DOFs
-    const int64_t *slice_ptr;  // [n_slices + 1] entry offsets, multiples of 32
-    const double *val;         // matrix values, sliced-ELL order
-    const int32_t *col;        // internal column ids, same order
-    const uint32_t *dir_mask;  // [n_slices] bit l set: row 32*s+l is a Dirichlet DOF
-    const double *M;           // lumped mass, internal order
-    const double *F;           // un-ramped load, internal order
+    int64_t n_rows;            // padded DOF rows = 3 * 32 * n_slices
+    int64_t n_slices;          // slices of 32 nodes
+    int64_t sh_slices;         // slices [0, sh_slices) hold the shared (interface) nodes
+    const int64_t *slice_ptr;  // [n_slices + 1] offsets in block-lanes (multiples of 32)
+    const double *val;         // block values, nine planes per block (see above)
+    const int32_t *col;        // internal column NODE ids
+    const uint32_t *dir_mask;  // bit (row & 31) of word (row >> 5) set: row is a Dirichlet DOF
+    const double *M;           // lumped mass, internal row order
+    const double *F;           // un-ramped load, internal row order
     double dt, dt2, dt_half, half_alpha, alpha;
 };
 
@@ -114,41 +127,59 @@ __device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p)
 // linear_ramp, commons.py:7-11
 __device__ __forceinline__ double saa_ramp(double t) { return (t <= 1.0) ? t : 1.0; }
 
-// Row sum of csr_matvec (Dynamic_solver.py:12): s = 0.0; s = s + (a_j * x[c_j]) in stored order.
-// Loads are issued UNROLL at a time ahead of the dependent add chain (memory-level parallelism);
-// the arithmetic order is untouched.
+// Row sums of csr_matvec (Dynamic_solver.py:12) for the three rows of one node:
+//   s_A = 0.0;  s_A = s_A + (a_j * x[c_j])  over the row's stored entries in order  (A = 0, 1, 2).
+// The loads of UNROLL blocks (9 values + 1 id + 3 gathered components each) are issued ahead of the dependent
+// add chains (memory-level parallelism); the arithmetic order is untouched.
 //   NC_X: the gathered vector is constant for the whole launch (per-step kernels) -> read-only path;
 //         the persistent kernel re-reads vectors other blocks wrote before the last grid barrier and
 //         must use ordinary (coherent after the barrier's fence) loads.
 template <int UNROLL, bool NC_X>
-__device__ __forceinline__ double saa_row_dot(const SaaDev &P, int64_t slice, int lane, const double *x)
+__device__ __forceinline__ void saa_node_dot(const SaaDev &P, int64_t slice, int lane, const double *x, double (&s)[3])
 {
     const int64_t beg = P.slice_ptr[slice];
     const int len = (int)((P.slice_ptr[slice + 1] - beg) >> 5);
-    const double *v = P.val + beg + lane;
+    const double *v = P.val + 9 * beg + lane;
     const int32_t *c = P.col + beg + lane;
-    double s = 0.0;
+    s[0] = 0.0; s[1] = 0.0; s[2] = 0.0;
     int j = 0;
     for (; j + UNROLL <= len; j += UNROLL) {
-        double a[UNROLL];
+        double a[UNROLL][9];
         int32_t k[UNROLL];
-        double xv[UNROLL];
+        double xv[UNROLL][3];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            a[u] = ld_stream_f64(v + 32 * (j + u));
             k[u] = ld_stream_s32(c + 32 * (j + u));
+#pragma unroll
+            for (int e = 0; e < 9; ++e) a[u][e] = ld_stream_f64(v + 32 * (9 * (j + u) + e));
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) xv[u] = NC_X ? __ldg(x + k[u]) : x[k[u]];
+        for (int u = 0; u < UNROLL; ++u) {
+            const double *xp = x + 3 * (int64_t)k[u];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) s = __dadd_rn(s, __dmul_rn(a[u], xv[u]));
+            for (int b = 0; b < 3; ++b) xv[u][b] = NC_X ? __ldg(xp + b) : xp[b];
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int A = 0; A < 3; ++A)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) s[A] = __dadd_rn(s[A], __dmul_rn(a[u][3 * A + b], xv[u][b]));
     }
     for (; j < len; ++j) {
-        double a = ld_stream_f64(v + 32 * j);
-        int32_t k = ld_stream_s32(c + 32 * j);
-        s = __dadd_rn(s, __dmul_rn(a, NC_X ? __ldg(x + k) : x[k]));
+        const int32_t k = ld_stream_s32(c + 32 * j);
+        double a[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a[e] = ld_stream_f64(v + 32 * (9 * j + e));
+        const double *xp = x + 3 * (int64_t)k;
+        double xv[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) xv[b] = NC_X ? __ldg(xp + b) : xp[b];
+#pragma unroll
+        for (int A = 0; A < 3; ++A)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) s[A] = __dadd_rn(s[A], __dmul_rn(a[3 * A + b], xv[b]));
     }
-    return s;
 }
 
 // Dynamic_solver.py:17 / :29 with Python's left-to-right association
@@ -165,13 +196,21 @@ __device__ __forceinline__ double saa_cd_update(const SaaDev &P, double Fi, doub
     return __ddiv_rn(num, den);
 }
 
-__device__ __forceinline__ void saa_finish_row(const SaaDev &P, int64_t slice, int lane, double Fi, const double *d0,
-                                               double *dn_d1, double ramp)
+__device__ __forceinline__ void saa_finish_row(const SaaDev &P, int64_t row, double Fi, const double *d0, double *dn_d1,
+                                               double ramp)
 {
-    const int64_t row = slice * 32 + lane;
     const double d1 = saa_cd_update(P, Fi, P.F[row], P.M[row], d0[row], dn_d1[row], ramp);
-    const bool clamp = (P.dir_mask[slice] >> lane) & 1u;
+    const bool clamp = (P.dir_mask[row >> 5] >> (row & 31)) & 1u;
     dn_d1[row] = clamp ? 0.0 : d1;                                               // :20 / :32
+}
+// the three rows of the node of (slice, lane);  ADD_ZERO: f_global = 0; f_global += f (Distributed_tools.py:84-86)
+template <bool ADD_ZERO>
+__device__ __forceinline__ void saa_finish_node(const SaaDev &P, int64_t slice, int lane, const double (&s)[3], const double *d0,
+                                                double *dn_d1, double ramp)
+{
+    const int64_t row0 = 3 * (slice * 32 + lane);
+#pragma unroll
+    for (int A = 0; A < 3; ++A) saa_finish_row(P, row0 + A, ADD_ZERO ? __dadd_rn(0.0, s[A]) : s[A], d0, dn_d1, ramp);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -193,9 +232,9 @@ __global__ void __launch_bounds__(256) saa_k_step(SaaDev P, int64_t slice_begin,
         clk_out->sync_step = clk_in->sync_step + (ADD_ZERO ? 1ull : 0ull);
     }
     if (slice >= slice_end) return;
-    double s = saa_row_dot<8, true>(P, slice, lane, d0);
-    if (ADD_ZERO) s = __dadd_rn(0.0, s);
-    saa_finish_row(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
+    double s[3];
+    saa_node_dot<SAA_UNROLL, true>(P, slice, lane, d0, s);
+    saa_finish_node<ADD_ZERO>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
 }
 
 // K2: partial internal force of the shared rows, stored for the own sum and packed into the messages
@@ -211,15 +250,19 @@ __global__ void __launch_bounds__(256) saa_k_boundary(SaaDev P, SaaHaloDev H, co
     unsigned long long step = 0;
     if (PEER) step = clk_in->sync_step;
     if (slice < P.sh_slices) {
-        const double s = saa_row_dot<8, true>(P, slice, lane, d0);
-        const int64_t row = slice * 32 + lane;
-        H.xbuf[row] = s;
-        for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
-            if (PEER) {
-                const int nb = H.dst_nb[k];
-                H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s;
-            } else {
-                H.sendbuf[H.dst_pos[k]] = s;
+        double s[3];
+        saa_node_dot<SAA_UNROLL, true>(P, slice, lane, d0, s);
+#pragma unroll
+        for (int A = 0; A < 3; ++A) {
+            const int64_t row = 3 * (slice * 32 + lane) + A;
+            H.xbuf[row] = s[A];
+            for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+                if (PEER) {
+                    const int nb = H.dst_nb[k];
+                    H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
+                } else {
+                    H.sendbuf[H.dst_pos[k]] = s[A];
+                }
             }
         }
     }
@@ -262,7 +305,7 @@ __global__ void __launch_bounds__(256) saa_k_shared_update(SaaDev P, SaaHaloDev 
         const double v = (s < H.sh_rows) ? H.xbuf[s] : *((const volatile double *)(recv + (s - H.sh_rows)));
         Fi = __dadd_rn(Fi, v);
     }
-    saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(clk_in->tn));
+    saa_finish_row(P, row, Fi, d0, dn_d1, saa_ramp(clk_in->tn));
 }
 
 // syn_cpus as a stand-alone operation (Distributed_tools.py:77-92) on a caller-provided force vector:
@@ -315,13 +358,17 @@ __global__ void __launch_bounds__(256) saa_k_step_fused(SaaDev P, SaaHaloDev H, 
         const int lane = threadIdx.x & 31;
         const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         if (slice >= P.n_slices) return;
-        double s = saa_row_dot<8, true>(P, slice, lane, d0);
+        double s[3];
+        saa_node_dot<SAA_UNROLL, true>(P, slice, lane, d0, s);
         if (slice < P.sh_slices) {
-            const int64_t row = slice * 32 + lane;
-            H.xbuf[row] = s;
-            for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
-                const int nb = H.dst_nb[k];
-                H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s;
+#pragma unroll
+            for (int A = 0; A < 3; ++A) {
+                const int64_t row = 3 * (slice * 32 + lane) + A;
+                H.xbuf[row] = s[A];
+                for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+                    const int nb = H.dst_nb[k];
+                    H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
+                }
             }
             __threadfence_system();
             __syncwarp();
@@ -335,8 +382,7 @@ __global__ void __launch_bounds__(256) saa_k_step_fused(SaaDev P, SaaHaloDev H, 
                 }
             }
         } else {
-            s = __dadd_rn(0.0, s);
-            saa_finish_row(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
+            saa_finish_node<true>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
         }
         return;
     }
@@ -353,7 +399,7 @@ __global__ void __launch_bounds__(256) saa_k_step_fused(SaaDev P, SaaHaloDev H, 
         const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
         Fi = __dadd_rn(Fi, v);
     }
-    saa_finish_row(P, row >> 5, (int)(row & 31), Fi, d0, dn_d1, saa_ramp(tn));
+    saa_finish_row(P, row, Fi, d0, dn_d1, saa_ramp(tn));
 }
 
 // Persistent variant of K1 (local mode): one cooperative launch runs n_steps time steps; u stays in HBM/L2,
@@ -371,8 +417,9 @@ __global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, 
     for (int64_t step = 0; step < n_steps; ++step) {
         const double ramp = saa_ramp(tn);
         for (int64_t slice = warp0; slice < P.n_slices; slice += nwarps) {
-            const double s = saa_row_dot<8, false>(P, slice, lane, d0);
-            saa_finish_row(P, slice, lane, s, d0, dn, ramp);
+            double s[3];
+            saa_node_dot<SAA_UNROLL, false>(P, slice, lane, d0, s);
+            saa_finish_node<false>(P, slice, lane, s, d0, dn, ramp);
         }
         tn = __dadd_rn(tn, P.dt);
         double *t = d0; d0 = dn; dn = t;
