@@ -275,12 +275,22 @@ def test_step_host_pipelined_chunks_equal_oracle():
     n = q["F"].size
     d0, dn, tn = rng.standard_normal(n) * 1e-3, rng.standard_normal(n) * 1e-3, 0.42
     o = fo.OracleProblem(len(pts), [r], pb["dt"], problem.DAMP_DEFAULT)
-    for _ in range(3):                                      # consecutive calls, rotating like Data_prepare.py:233-235
+    import torch
+    bufs = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(3)]   # page-locked: graph-replayed pipeline
+    bufs[0][:], bufs[1][:] = d0, dn
+    d0, dn, out = bufs
+    for _ in range(7):                                      # consecutive calls, rotating like Data_prepare.py:233-235
         o.set_state(0, d0, dn, tn)
         o.run(1, model=True)
-        d1 = pl.step_host(d0, dn, tn, splan.MODE_LOCAL)
+        d1 = pl.step_host(d0, dn, tn, splan.MODE_LOCAL, out=out)
         assert bits_equal(d1, o.d0(0))
-        dn, d0, tn = d0, d1, tn + float(pb["dt"])
+        dn, d0, out, tn = d0, d1, dn, tn + float(pb["dt"])
+    # pageable buffers take the plain path and give the same numbers
+    d1 = pl.step_host(d0.copy(), dn.copy(), tn, splan.MODE_LOCAL)
+    o.set_state(0, d0, dn, tn)
+    o.run(1, model=True)
+    assert bits_equal(d1, o.d0(0))
+    dn, d0, tn = d0.copy(), d1, tn + float(pb["dt"])
     # the resident state after a host call is (d1, d0, tn + dt): continue on the device
     pl.step(5, splan.MODE_LOCAL)
     pl.synchronize()
