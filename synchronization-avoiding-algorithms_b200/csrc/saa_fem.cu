@@ -157,13 +157,6 @@ struct saa_plan {
     saa_ncclComm_t comm = nullptr;
     saa_group *group = nullptr;
     cudaEvent_t ev_msg = nullptr;
-    // pipelined host call (saa_step_host without interface rows)
-    bool host_pipeline = true;              // SAA_HOST_PIPELINE=0 disables it
-    cudaStream_t stream_in = nullptr, stream_out = nullptr;
-    cudaEvent_t ev_d0 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_dn[8] = {}, ev_k[8] = {};
-    double *h_tn = nullptr;                 // pinned scalar the captured pipeline reads tn from
-    struct HostGraph { const double *d0, *dn; double *d1; int cur; cudaGraphExec_t exec; int kernels; };
-    std::vector<HostGraph> host_graphs;
     bool in_split_step = false;             // between saa_plan_step_begin_host and saa_plan_step_end_host
     double *d_force = nullptr;              // [2 * n_rows] scratch of the stand-alone force synchronisation
 };
@@ -480,10 +473,6 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     std::vector<int32_t>().swap(p->indptr); std::vector<int32_t>().swap(p->indices);
     std::vector<double>().swap(p->data); std::vector<double>().swap(p->F); std::vector<double>().swap(p->M);
     CK(cudaDeviceSynchronize());   // set-up work ran on the default stream; the plan's stream is non-blocking
-    {
-        const char *e = getenv("SAA_HOST_PIPELINE");
-        p->host_pipeline = !(e && e[0] == '0');
-    }
     p->finalized = true;
     return 0;
 }
@@ -507,17 +496,6 @@ extern "C" int saa_plan_destroy(saa_plan *p)
             if (q) cudaFree(q);
         if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
         if (p->ev_msg) cudaEventDestroy(p->ev_msg);
-        if (p->ev_d0) cudaEventDestroy(p->ev_d0);
-        if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-        if (p->ev_join) cudaEventDestroy(p->ev_join);
-        for (auto &g : p->host_graphs) cudaGraphExecDestroy(g.exec);
-        if (p->h_tn) cudaFreeHost(p->h_tn);
-        for (int i = 0; i < 8; ++i) {
-            if (p->ev_dn[i]) cudaEventDestroy(p->ev_dn[i]);
-            if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
-        }
-        if (p->stream_in) cudaStreamDestroy(p->stream_in);
-        if (p->stream_out) cudaStreamDestroy(p->stream_out);
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;
@@ -897,112 +875,13 @@ extern "C" int saa_plan_synchronize(saa_plan *p)
     return 0;
 }
 
-// Pipelined host call for a partition without interface rows (size == 1): after d0 is on the device, dn is
-// uploaded in SAA_HOST_CHUNKS row ranges; as soon as a range has arrived its slices are stepped and its part of
-// d1 starts travelling back, so the dn upload, the kernels and the d1 download overlap (PCIe is full duplex).
-// Row ranges are whole sorting windows: the layout permutes rows only inside a window, so an external row
-// range maps onto a range of slices.
-#define SAA_HOST_CHUNKS 6
-// enqueue the whole pipeline; called under stream capture (fork from / join into the plan's stream)
-static int enqueue_host_pipeline(saa_plan *p, const double *d0, const double *dn, double *d1)
-{
-    const int64_t n = p->n_dof, nn = n / 3;
-    const int64_t windows = (nn + SAA_SIGMA - 1) / SAA_SIGMA;
-    const int C = (int)std::min<int64_t>(SAA_HOST_CHUNKS, windows);
-    double *cur0 = p->d_buf[p->cur], *cur1 = p->d_buf[p->cur ^ 1];
-    cudaStream_t sin = p->stream_in, sk = p->stream, sout = p->stream_out;
-    CK(cudaEventRecord(p->ev_fork, sk));
-    CK(cudaStreamWaitEvent(sin, p->ev_fork, 0));
-    CK(cudaStreamWaitEvent(sout, p->ev_fork, 0));
-    CK(cudaMemcpyAsync(&p->d_clk[p->cur].tn, p->h_tn, sizeof(double), cudaMemcpyHostToDevice, sin));
-    CK(cudaMemcpyAsync(p->d_stage, d0, n * sizeof(double), cudaMemcpyHostToDevice, sin));
-    saa_k_scatter_to_internal<<<nblk(n, 256), 256, 0, sin>>>(n, p->d_iperm, p->d_stage, cur0);
-    CK(cudaEventRecord(p->ev_d0, sin));
-    CK(cudaStreamWaitEvent(sk, p->ev_d0, 0));
-    for (int c = 0; c < C; ++c) {
-        const int64_t w0 = windows * c / C, w1 = windows * (c + 1) / C;
-        const int64_t r0 = 3 * SAA_SIGMA * w0, r1 = std::min<int64_t>(n, 3 * SAA_SIGMA * w1);
-        const int64_t s0 = (SAA_SIGMA / 32) * w0, s1 = std::min<int64_t>(p->n_slices, (SAA_SIGMA / 32) * w1);
-        CK(cudaMemcpyAsync(p->d_stage + n + r0, dn + r0, (r1 - r0) * sizeof(double), cudaMemcpyHostToDevice, sin));
-        saa_k_scatter_to_internal<<<nblk(r1 - r0, 256), 256, 0, sin>>>(r1 - r0, p->d_iperm + r0, p->d_stage + n + r0, cur1);
-        CK(cudaEventRecord(p->ev_dn[c], sin));
-        CK(cudaStreamWaitEvent(sk, p->ev_dn[c], 0));
-        saa_k_step<false><<<nblk(s1 - s0, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, sk>>>(
-            p->D, s0, s1, cur0, cur1, p->d_clk + p->cur, (c == C - 1) ? p->d_clk + (p->cur ^ 1) : nullptr);
-        CK(cudaEventRecord(p->ev_k[c], sk));
-        CK(cudaStreamWaitEvent(sout, p->ev_k[c], 0));
-        saa_k_gather_to_external<<<nblk(r1 - r0, 256), 256, 0, sout>>>(r1 - r0, p->d_iperm + r0, cur1, p->d_stage + 2 * n + r0);
-        CK(cudaMemcpyAsync(d1 + r0, p->d_stage + 2 * n + r0, (r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, sout));
-    }
-    CK(cudaEventRecord(p->ev_join, sout));
-    CK(cudaStreamWaitEvent(sk, p->ev_join, 0));
-    return 2 + 3 * C;    // kernels in the pipeline
-}
-
-// The caller's loop rotates a handful of host buffers (d_n = d_0; d_0 = d1), so the pipeline is captured once per
-// (d0, dn, d1, buffer parity) combination into a CUDA graph and replayed: one launch call per step instead of ~60.
-static int step_host_pipelined(saa_plan *p, const double *d0, const double *dn, double tn, double *d1)
-{
-    if (!p->stream_in) {
-        CK(cudaStreamCreateWithFlags(&p->stream_in, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&p->stream_out, cudaStreamNonBlocking));
-        cudaEvent_t *evs[] = {&p->ev_d0, &p->ev_fork, &p->ev_join};
-        for (cudaEvent_t *e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        for (int c = 0; c < SAA_HOST_CHUNKS; ++c) {
-            CK(cudaEventCreateWithFlags(&p->ev_dn[c], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&p->ev_k[c], cudaEventDisableTiming));
-        }
-        CK(cudaHostAlloc((void **)&p->h_tn, sizeof(double), cudaHostAllocDefault));
-    }
-    *p->h_tn = tn;
-    saa_plan::HostGraph *hit = nullptr;
-    for (auto &g : p->host_graphs)
-        if (g.d0 == d0 && g.dn == dn && g.d1 == d1 && g.cur == p->cur) hit = &g;
-    if (!hit) {
-        if (p->host_graphs.size() >= 12) {                    // a caller that never reuses buffers: drop the oldest
-            cudaGraphExecDestroy(p->host_graphs.front().exec);
-            p->host_graphs.erase(p->host_graphs.begin());
-        }
-        saa_plan::HostGraph g{d0, dn, d1, p->cur, nullptr, 0};
-        cudaGraph_t graph;
-        CK(cudaStreamSynchronize(p->stream));
-        CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-        const int k = enqueue_host_pipeline(p, d0, dn, d1);
-        cudaError_t e = cudaStreamEndCapture(p->stream, &graph);
-        if (k < 0 || e != cudaSuccess) return fail("saa_step_host: capturing the pipelined call failed (%s)", cudaGetErrorString(e));
-        g.kernels = k;
-        CK(cudaGraphInstantiate(&g.exec, graph, 0));
-        CK(cudaGraphDestroy(graph));
-        p->host_graphs.push_back(g);
-        hit = &p->host_graphs.back();
-    }
-    CK(cudaGraphLaunch(hit->exec, p->stream));
-    p->launches += hit->kernels;
-    p->cur ^= 1;
-    p->step_index++;
-    CK(cudaStreamSynchronize(p->stream));
-    return 0;
-}
-
 extern "C" int saa_step_host(saa_plan *p, const double *d0, const double *dn, double tn, int mode, double *d1)
 {
     NEED_FINAL(p, "saa_step_host");
     if (!d0 || !dn || !d1) return fail("saa_step_host: null argument");
     CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->group ? p->group->stream : p->stream;
     if (p->group) return fail("saa_step_host: plan belongs to a group");
-    const bool local = (mode == SAA_MODE_LOCAL) || (mode == SAA_MODE_SYNC && p->size == 1);
-    if (local && p->sh_slices == 0 && p->hist_cap == 0 && p->host_pipeline) {
-        // the captured pipeline needs page-locked host buffers (pageable copies are staged synchronously)
-        bool pinned = true;
-        const void *hp[3] = {d0, dn, d1};
-        for (const void *q : hp) {
-            cudaPointerAttributes a;
-            if (cudaPointerGetAttributes(&a, q) != cudaSuccess || a.type != cudaMemoryTypeHost) pinned = false;
-        }
-        cudaGetLastError();
-        if (pinned) return step_host_pipelined(p, d0, dn, tn, d1);
-    }
-    cudaStream_t st = p->stream;
     CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
     if (set_state_from_stage(p, st, tn)) return -1;

@@ -259,41 +259,3 @@ def test_one_process_per_gpu_transports(transport, name, n):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(f"ok ({transport})") == n
-
-
-def test_step_host_pipelined_chunks_equal_oracle():
-    """saa_step_host on a partition without interface rows pipelines the dn upload, the slices and the d1 download
-    in several row chunks (whole sorting windows); the result is still one reference call, bit for bit."""
-    pts, cells, fac = mesh.structured_beam(6)              # 6 517 nodes -> 7 windows of 1024 nodes -> 6 chunks
-    pb = problem.build_problem(pts, cells, fac, np.zeros(len(cells), dtype=np.int64), 1)
-    q = pb["ranks"][0]
-    pl = problem.make_plan(q, pb["dt"], problem.DAMP_DEFAULT, 1)
-    fo = oracle_module()
-    r = dict(K_indptr=q["K"].indptr, K_indices=q["K"].indices, K_data=q["K"].data, F=q["F"], lM=q["lM"],
-             dirichlet=q["dirichlet"], nodes=q["nodes"])
-    rng = np.random.default_rng(3)
-    n = q["F"].size
-    d0, dn, tn = rng.standard_normal(n) * 1e-3, rng.standard_normal(n) * 1e-3, 0.42
-    o = fo.OracleProblem(len(pts), [r], pb["dt"], problem.DAMP_DEFAULT)
-    import torch
-    bufs = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(3)]   # page-locked: graph-replayed pipeline
-    bufs[0][:], bufs[1][:] = d0, dn
-    d0, dn, out = bufs
-    for _ in range(7):                                      # consecutive calls, rotating like Data_prepare.py:233-235
-        o.set_state(0, d0, dn, tn)
-        o.run(1, model=True)
-        d1 = pl.step_host(d0, dn, tn, splan.MODE_LOCAL, out=out)
-        assert bits_equal(d1, o.d0(0))
-        dn, d0, out, tn = d0, d1, dn, tn + float(pb["dt"])
-    # pageable buffers take the plain path and give the same numbers
-    d1 = pl.step_host(d0.copy(), dn.copy(), tn, splan.MODE_LOCAL)
-    o.set_state(0, d0, dn, tn)
-    o.run(1, model=True)
-    assert bits_equal(d1, o.d0(0))
-    dn, d0, tn = d0.copy(), d1, tn + float(pb["dt"])
-    # the resident state after a host call is (d1, d0, tn + dt): continue on the device
-    pl.step(5, splan.MODE_LOCAL)
-    pl.synchronize()
-    o.set_state(0, d0, dn, tn)
-    o.run(5)
-    assert bits_equal(pl.d0(), o.d0(0))
