@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo transport for N > 1")
     ap.add_argument("--sync-avoid", default="", help="N > 1: also time the synchronization-avoiding loop (BASELINE config 5); "
                     "comma list of re-sync periods k, 0 = never re-synchronise (the reference's behaviour), e.g. 0,10,50")
+    ap.add_argument("--balance", action="store_true", help="N > 1: size the x-slabs by each GPU's measured speed (a short local "
+                    "run first), so that a slower GPU does not pace the others")
     ap.add_argument("--filter-size", type=int, default=150, help="n_s of the LSTM refill (Online_predictor.py:57)")
     return ap.parse_args()
 
@@ -303,10 +305,26 @@ def main():
     e2e_steps = args.e2e_steps or (200 if m <= 32 else 30)
     want_cpu = (not args.no_cpu_baseline) and world == 1
     t_setup = time.time()
+    balance = None
     if args.setup == "host":
         pl, info = setup_host(m, world, rank, local)
     else:
         pl, info = setup_device(m, world, rank, local, keep_csr=want_cpu and m <= 32)
+        if world > 1 and args.balance:
+            # pass 1 built equal slabs: time them without any exchange, then rebuild with layers ~ measured speed
+            from saa_b200 import device_setup
+            st0 = torch.cuda.ExternalStream(pl.stream, device=torch.device("cuda", local))
+            ms0, _ = time_resident(pl, torch, st0, 300, 30, splan.MODE_LOCAL, splan.LAUNCH_AUTO, lambda: torch.cuda.synchronize())
+            speed = torch.tensor([pl.n_dof / ms0], dtype=torch.float64, device="cuda")
+            allv = [torch.zeros_like(speed) for _ in range(world)]
+            dist.all_gather(allv, speed)
+            balance = [float(v.item()) for v in allv]
+            pl.close()
+            del pl
+            torch.cuda.empty_cache()
+            device_setup.set_layer_weights(balance)
+            pl, info = setup_device(m, world, rank, local)
+            balance = [b / max(balance) for b in balance]
     transport = multi.attach_transport(pl, args.transport) if world > 1 else "none"
     t_setup = time.time() - t_setup
     n_dof_global = 3 * info["n_nodes"]
@@ -395,7 +413,7 @@ def main():
             "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(m, n_dof_global, info["n_elem"]),
-                       "partition": info["part"], "transport": transport, "assembly": info["assembly"],
+                       "partition": info["part"], "balance": balance, "transport": transport, "assembly": info["assembly"],
                        "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
                        "launch": args.launch, "dt": dtv, "setup_s": round(t_setup, 1),
                        "l2": "inputs larger than L2: matrix stream per step per GPU = %.0f MB vs 126 MB L2" % (pl.matrix_bytes / 1e6)},

@@ -23,9 +23,26 @@ from .problem import DAMP_DEFAULT, E_DEFAULT, FZ_DEFAULT, GAMMA_DEFAULT, NU_DEFA
 
 
 # ---- structured cantilever, one x-slab per rank ------------------------------------------------------------
+_LAYER_WEIGHTS = None     # optional relative speeds of the ranks (set_layer_weights): faster GPUs get more layers
+
+
+def set_layer_weights(weights):
+    """Relative throughput of every rank (e.g. measured DOF-steps/s of a short local run).  None = equal slabs."""
+    global _LAYER_WEIGHTS
+    _LAYER_WEIGHTS = None if weights is None else [float(w) for w in weights]
+
+
 def layer_bounds(m, size, length=25):
     """Hexahedron layers (index along x) of each rank: rank r owns layers [b[r], b[r+1])."""
     nx = length * m
+    if _LAYER_WEIGHTS is not None and len(_LAYER_WEIGHTS) == size:
+        w = np.asarray(_LAYER_WEIGHTS) / np.sum(_LAYER_WEIGHTS)
+        b = np.rint(np.concatenate([[0.0], np.cumsum(w)]) * nx).astype(int)
+        b[0], b[-1] = 0, nx
+        for r in range(1, size + 1):              # every rank keeps at least one layer
+            b[r] = max(b[r], b[r - 1] + 1)
+        b[-1] = nx
+        return [int(x) for x in b]
     return [(r * nx) // size for r in range(size + 1)]
 
 
