@@ -350,6 +350,11 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches = time_resident(pl, torch, stream, steps, args.warmup, mode, launch, barrier)
     ms = max_over_ranks(ms)
+    ms_local = None
+    if world > 1:   # the same shards stepped WITHOUT the exchange (MODEL=True arithmetic): what the halo costs per step
+        k_loc = min(steps, 500)
+        ms_local, _ = time_resident(pl, torch, stream, k_loc, 20, splan.MODE_LOCAL, launch, barrier)
+        ms_local = max_over_ranks(ms_local) / k_loc
 
     # ---- end to end through the reference-facing host call -----------------------------------------
     d0, dn, tn = pl.get_state()
@@ -415,7 +420,7 @@ def main():
             "config": {"workload": workload_name(m, n_dof_global, info["n_elem"]),
                        "partition": info["part"], "balance": balance, "transport": transport, "assembly": info["assembly"],
                        "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
-                       "launch": args.launch, "dt": dtv, "setup_s": round(t_setup, 1),
+                       "launch": args.launch, "dt": dtv, "setup_s": round(t_setup, 1), "ms_per_step_without_exchange": ms_local,
                        "l2": "inputs larger than L2: matrix stream per step per GPU = %.0f MB vs 126 MB L2" % (pl.matrix_bytes / 1e6)},
             "e2e": {"value": n_dof_global * e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",
                     "h2d_bytes_per_step": 2 * 8 * n_dof_local, "d2h_bytes_per_step": 8 * n_dof_local,

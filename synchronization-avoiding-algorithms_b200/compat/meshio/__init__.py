@@ -1,6 +1,8 @@
 """Stand-in for meshio (legacy ASCII VTK only): see compat/README.md."""
 import numpy as np
 
+import _saa_bootstrap  # noqa: F401
+
 from saa_b200 import mesh as _mesh
 
 

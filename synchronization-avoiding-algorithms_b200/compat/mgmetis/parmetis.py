@@ -3,6 +3,8 @@ chunk of elements; the chunks are gathered, partitioned by serial METIS (dual gr
 each rank gets the part vector of its own chunk back, like ParMETIS_V3_PartMeshKway."""
 import numpy as np
 
+import _saa_bootstrap  # noqa: F401
+
 from saa_b200 import comm as _comm
 from saa_b200 import partition as _partition
 
