@@ -20,6 +20,7 @@
 
 #define SAA_SIGMA 1024          // nodes per sorting window (multiple of 32)
 #define SAA_WARPS_PER_BLOCK 8
+#define SAA_DEFAULT_KVARIANT (-1) // schedule variant of the step kernel: -1 = by partition size; SAA_KVARIANT overrides
 
 static thread_local std::string g_err;
 
@@ -125,6 +126,7 @@ struct saa_plan {
     double *d_recv = nullptr;               // peer region: [2 parities x total_msg doubles | n_nb arrival flags (u64)]
     unsigned int *d_done = nullptr;          // [0] boundary completion counter, [1] error word
     unsigned long long *d_own_ready = nullptr;
+    int kvariant = SAA_DEFAULT_KVARIANT;    // SAA_KVARIANT: schedule variant of the step kernel
     bool peer_fused = true;                 // one fused launch per synchronised step (SAA_PEER_FUSED=0: three kernels)
     int32_t *d_dst_nb = nullptr;
     // peer-memory transport
@@ -473,6 +475,10 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     std::vector<int32_t>().swap(p->indptr); std::vector<int32_t>().swap(p->indices);
     std::vector<double>().swap(p->data); std::vector<double>().swap(p->F); std::vector<double>().swap(p->M);
     CK(cudaDeviceSynchronize());   // set-up work ran on the default stream; the plan's stream is non-blocking
+    if (const char *kv = getenv("SAA_KVARIANT")) p->kvariant = atoi(kv);
+    // measured on B200 (profiles/r1/kernel_variants.md): below ~4 M rows per GPU the 3-blocks-per-SM plain schedule wins,
+    // above it the column-prefetching one with 4 blocks per SM
+    if (p->kvariant < 0) p->kvariant = (p->n_dof < 4000000) ? 2 : 4;
     p->finalized = true;
     return 0;
 }
@@ -679,12 +685,36 @@ static int after_step(saa_plan *p, cudaStream_t st, int mode)
 }
 
 // ---- stepping --------------------------------------------------------------------------------------------
+// instruction-schedule variants of the step kernel (same arithmetic, same bits): dot mode x minimum blocks per SM.
+// Which one is fastest depends on the schedule ptxas happens to pick; profiles/r1/kernel_variants.md has the
+// measurements behind the default.
+static void launch_step_kernel(int variant, unsigned grid, cudaStream_t st, const SaaDev &D, const SaaHaloDev &H, const double *d0,
+                               double *dn, const SaaClock *ci, SaaClock *co, int64_t slice_begin, unsigned n_main, unsigned count_sync)
+{
+    switch (variant) {
+    case 0: saa_k_step<0, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    case 1: saa_k_step<0, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    case 2: saa_k_step<0, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    case 3: saa_k_step<1, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    case 5: saa_k_step<1, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    }
+}
+// K1 only: slices [slice_begin, n_slices) as interior rows (no interface handling inside the kernel)
+static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, unsigned count_sync, bool advance_clock)
+{
+    SaaDev D = p->D;
+    D.sh_slices = 0;
+    const unsigned n_main = std::max(1u, nblk(p->n_slices - slice_begin, SAA_WARPS_PER_BLOCK));
+    launch_step_kernel(p->kvariant, n_main, st, D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
+                       advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, n_main, count_sync);
+    p->launches++;
+}
+
 static void launch_local_step(saa_plan *p, cudaStream_t st)
 {
-    saa_k_step<false><<<nblk(p->n_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
-        p->D, 0, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1));
+    launch_interior(p, st, 0, 0u, true);
     p->cur ^= 1;
-    p->launches++;
 }
 
 static bool needs_hooks(const saa_plan *p, int mode) { return mode == SAA_MODE_PREDICT || p->hist_cap > 0; }
@@ -753,11 +783,8 @@ static void sync_phase_boundary(saa_plan *p, cudaStream_t st)
 }
 static void sync_phase_interior(saa_plan *p, cudaStream_t st)
 {
-    // also advances tn; runs even with zero interior slices so that tn moves
-    const int64_t n_in = p->n_slices - p->sh_slices;
-    saa_k_step<true><<<std::max(1u, nblk(n_in, SAA_WARPS_PER_BLOCK)), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
-        p->D, p->sh_slices, p->n_slices, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1));
-    p->launches++;
+    // also advances the clock; runs even with zero interior slices so that tn moves
+    launch_interior(p, st, p->sh_slices, 1u, true);
 }
 static void sync_phase_shared(saa_plan *p, cudaStream_t st)
 {
@@ -800,8 +827,8 @@ static void launch_peer_step(saa_plan *p, cudaStream_t st)
     if (p->peer_fused && p->sh_slices > 0) {
         const unsigned n_main = nblk(p->n_slices, SAA_WARPS_PER_BLOCK);
         const unsigned n_tail = nblk(p->H.sh_rows, 256);
-        saa_k_step_fused<<<n_main + n_tail, 256, 0, st>>>(p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
-                                                         p->d_clk + (p->cur ^ 1), n_main);
+        launch_step_kernel(p->kvariant, n_main + n_tail, st, p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
+                           p->d_clk + (p->cur ^ 1), 0, n_main, 1u);
         p->launches++;
         p->cur ^= 1;
         return;
@@ -1099,8 +1126,12 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
         cudaIpcMemHandle_t h;
         memcpy(&h, (const char *)handles64 + 64 * k, sizeof h);
         void *ptr = nullptr;
-        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-        p->peer_mapped.push_back(ptr);
+        if (getenv("SAA_DEBUG_PEER_SELF")) {
+            ptr = p->d_recv;                          // single-GPU timing probe: "the neighbour" is this plan itself
+        } else {
+            CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            p->peer_mapped.push_back(ptr);
+        }
         if (remote_slot[k] < 0 || remote_slot[k] >= remote_n_nb[k]) return fail("saa_plan_peer_attach: bad remote slot");
         recv[k] = (double *)ptr;
         stride[k] = remote_total[k];
@@ -1120,6 +1151,8 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
     p->Hp.peer_recv = p->d_peer_recv; p->Hp.peer_stride = p->d_peer_stride; p->Hp.peer_flag = p->d_peer_flag;
     const char *fz = getenv("SAA_PEER_FUSED");
     p->peer_fused = !(fz && fz[0] == '0');
+    const char *dbg = getenv("SAA_DEBUG_PEER");        // timing experiments only: results are wrong when set
+    p->Hp.dbg = dbg ? atoi(dbg) : 0;
     p->peer = true;
     return 0;
 }

@@ -32,6 +32,9 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef SAA_DOT_MODE
+#define SAA_DOT_MODE 0
+#endif
 #ifndef SAA_UNROLL
 #define SAA_UNROLL 2          // blocks whose loads are in flight together per thread (2 x 76 B x 32 lanes per warp)
 #endif
@@ -77,6 +80,8 @@ struct SaaHaloDev {
     unsigned int *done_ctr;                 // blocks of the pack kernel that have finished (last one raises the flags)
     unsigned long long *own_ready;          // fused step: number of steps whose own boundary forces are complete
     unsigned int *err;                      // set when a bounded wait expired (a peer never delivered)
+    int dbg;                                // timing experiments only (SAA_DEBUG_PEER): 1 no waits, 2 local stores,
+                                            // 4 skip the tail blocks, 8 treat boundary slices as interior
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
@@ -134,8 +139,70 @@ __device__ __forceinline__ double saa_ramp(double t) { return (t <= 1.0) ? t : 1
 //   NC_X: the gathered vector is constant for the whole launch (per-step kernels) -> read-only path;
 //         the persistent kernel re-reads vectors other blocks wrote before the last grid barrier and
 //         must use ordinary (coherent after the barrier's fence) loads.
+// Scheduling fence: every value listed must be in its register before any instruction after this point issues,
+// and nothing after it may be hoisted above it.  Used to make ALL loads of a batch issue back to back (the
+// compiler otherwise interleaves each dependent multiply-add right behind its own load, which stalls the warp on
+// the first outstanding load and leaves only 3-4 requests in flight).
+#define SAA_FENCE9(a) asm volatile("" : "+d"(a[0]), "+d"(a[1]), "+d"(a[2]), "+d"(a[3]), "+d"(a[4]), "+d"(a[5]), "+d"(a[6]), "+d"(a[7]), "+d"(a[8]))
+#define SAA_FENCE3(x) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]))
+
+template <bool NC_X>
+__device__ __forceinline__ void saa_gather3(const double *x, int32_t k, double (&xv)[3])
+{
+    const double *xp = x + 3 * (int64_t)k;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) xv[b] = NC_X ? __ldg(xp + b) : xp[b];
+}
+// s_A = s_A + a[A][b]*x[b], b = 0,1,2: separately rounded multiply and add, ascending column order
+__device__ __forceinline__ void saa_block_madd(const double (&a)[9], const double (&xv)[3], double (&s)[3])
+{
+#pragma unroll
+    for (int A = 0; A < 3; ++A)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) s[A] = __dadd_rn(s[A], __dmul_rn(a[3 * A + b], xv[b]));
+}
+
 template <int UNROLL, bool NC_X>
-__device__ __forceinline__ void saa_node_dot(const SaaDev &P, int64_t slice, int lane, const double *x, double (&s)[3])
+__device__ __forceinline__ void saa_node_dot_pipe(const SaaDev &P, int64_t slice, int lane, const double *x, double (&s)[3])
+{
+    static_assert(UNROLL == 2, "the software pipeline below is written for two blocks per batch");
+    const int64_t beg = P.slice_ptr[slice];
+    const int len = (int)((P.slice_ptr[slice + 1] - beg) >> 5);
+    const double *v = P.val + 9 * beg + lane;
+    const int32_t *c = P.col + beg + lane;
+    s[0] = 0.0; s[1] = 0.0; s[2] = 0.0;
+    // column ids run one batch ahead of the values, so that the gathers of a batch are issued together with its
+    // value loads instead of after a first round trip
+    int32_t k0 = 0, k1 = 0;
+    if (len > 0) k0 = ld_stream_s32(c);
+    if (len > 1) k1 = ld_stream_s32(c + 32);
+    int j = 0;
+    for (; j + 2 <= len; j += 2) {
+        double a0[9], a1[9], x0[3], x1[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a0[e] = ld_stream_f64(v + 32 * (9 * j + e));
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a1[e] = ld_stream_f64(v + 32 * (9 * (j + 1) + e));
+        saa_gather3<NC_X>(x, k0, x0);
+        saa_gather3<NC_X>(x, k1, x1);
+        if (j + 2 < len) k0 = ld_stream_s32(c + 32 * (j + 2));
+        if (j + 3 < len) k1 = ld_stream_s32(c + 32 * (j + 3));
+        SAA_FENCE9(a0); SAA_FENCE9(a1); SAA_FENCE3(x0); SAA_FENCE3(x1);
+        saa_block_madd(a0, x0, s);              // blocks in ascending column order: the order of the CSR row
+        saa_block_madd(a1, x1, s);
+    }
+    if (j < len) {
+        double a0[9], x0[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a0[e] = ld_stream_f64(v + 32 * (9 * j + e));
+        saa_gather3<NC_X>(x, k0, x0);
+        saa_block_madd(a0, x0, s);
+    }
+}
+
+// plain form: the compiler schedules the loads of UNROLL blocks against the dependent add chains
+template <int UNROLL, bool NC_X>
+__device__ __forceinline__ void saa_node_dot_simple(const SaaDev &P, int64_t slice, int lane, const double *x, double (&s)[3])
 {
     const int64_t beg = P.slice_ptr[slice];
     const int len = (int)((P.slice_ptr[slice + 1] - beg) >> 5);
@@ -182,6 +249,15 @@ __device__ __forceinline__ void saa_node_dot(const SaaDev &P, int64_t slice, int
     }
 }
 
+// MODE 0: plain loop, 1: column ids prefetched one batch ahead (both give the same bits; which one is faster is a
+// matter of the instruction schedule ptxas picks, see profiles/)
+template <int MODE, bool NC_X>
+__device__ __forceinline__ void saa_node_dot(const SaaDev &P, int64_t slice, int lane, const double *x, double (&s)[3])
+{
+    if (MODE == 0) saa_node_dot_simple<SAA_UNROLL, NC_X>(P, slice, lane, x, s);
+    else saa_node_dot_pipe<SAA_UNROLL, NC_X>(P, slice, lane, x, s);
+}
+
 // Dynamic_solver.py:17 / :29 with Python's left-to-right association
 __device__ __forceinline__ double saa_cd_update(const SaaDev &P, double Fi, double F, double M, double d0, double dn,
                                                 double ramp)
@@ -214,28 +290,12 @@ __device__ __forceinline__ void saa_finish_node(const SaaDev &P, int64_t slice, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1: fused force + update over slices [slice_begin, slice_end).  One warp per slice.
-//   ADD_ZERO: the synchronised path routes every force through f_global = 0; f_global += f
-//             (Distributed_tools.py:84-86), i.e. F_int = 0.0 + s; the local path uses s itself.
-// d1 overwrites dn in place (row i only needs its own dn[i]).  The clock is read from device memory so that
-// the launch can be replayed from a CUDA graph; block 0 writes tn + dt for the next step (:235) and, on the
-// synchronised path, counts the step.
-template <bool ADD_ZERO>
-__global__ void __launch_bounds__(256) saa_k_step(SaaDev P, int64_t slice_begin, int64_t slice_end, const double *__restrict__ d0,
-                                                  double *__restrict__ dn_d1, const SaaClock *clk_in, SaaClock *clk_out)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t slice = slice_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const double tn = clk_in->tn;
-    if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-        clk_out->tn = __dadd_rn(tn, P.dt);
-        clk_out->sync_step = clk_in->sync_step + (ADD_ZERO ? 1ull : 0ull);
-    }
-    if (slice >= slice_end) return;
-    double s[3];
-    saa_node_dot<SAA_UNROLL, true>(P, slice, lane, d0, s);
-    saa_finish_node<ADD_ZERO>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
-}
+// K1 is the interior path of saa_k_step (below): fused force + update, one warp per slice of 32 nodes.  d1
+// overwrites dn in place (row i only needs its own dn[i]).  The clock is read from device memory so that the
+// launch can be replayed from a CUDA graph; block 0 writes tn + dt for the next step (Data_prepare.py:235).
+// On the synchronised path every force passes through f_global = 0; f_global += f (Distributed_tools.py:84-86),
+// i.e. F_int = 0.0 + s; a row sum that starts at +0.0 can never be -0.0, so 0.0 + s == s bit for bit and the
+// same code serves the local path.
 
 // K2: partial internal force of the shared rows, stored for the own sum and packed into the messages
 // of every neighbour holding the node (fused halo pack).
@@ -251,7 +311,7 @@ __global__ void __launch_bounds__(256) saa_k_boundary(SaaDev P, SaaHaloDev H, co
     if (PEER) step = clk_in->sync_step;
     if (slice < P.sh_slices) {
         double s[3];
-        saa_node_dot<SAA_UNROLL, true>(P, slice, lane, d0, s);
+        saa_node_dot<SAA_DOT_MODE, true>(P, slice, lane, d0, s);
 #pragma unroll
         for (int A = 0; A < 3; ++A) {
             const int64_t row = 3 * (slice * 32 + lane) + A;
@@ -335,7 +395,9 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
     out[row] = Fi;
 }
 
-// K1+K2+K3 in ONE launch per synchronised step (peer transport).  Blocks are dispatched in index order, so
+// THE step kernel.  Local steps and the interior phase of the staged transports run it with sh_slices = 0 and
+// no tail blocks (pure K1 over slices [slice_begin, n_slices)).  With the peer transport it is K1+K2+K3 in ONE
+// launch per synchronised step: blocks are dispatched in index order, so
 //   * the first blocks own the boundary slices (internal order is boundary-first): partial forces -> own buffer
 //     and straight into the neighbours' receive areas; the warp that completes the last boundary slice raises
 //     the neighbours' arrival flags (system scope) and the local "own forces ready" flag;
@@ -344,33 +406,36 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
 //   * the last few blocks (index >= n_main) wait for the arrival flags, then do the rank-ordered sum and the
 //     update of the shared rows.
 // Same arithmetic, same order as the three-kernel sequence — one launch gap and no pipeline drain per step.
-__global__ void __launch_bounds__(256) saa_k_step_fused(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
+//   count_sync: 1 on synchronised steps (advances the exchange counter), 0 on local ones.
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
                                                         double *__restrict__ dn_d1, const SaaClock *clk_in, SaaClock *clk_out,
-                                                        unsigned int n_main)
+                                                        int64_t slice_begin, unsigned int n_main, unsigned int count_sync)
 {
     const unsigned long long step = clk_in->sync_step;
     const double tn = clk_in->tn;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         clk_out->tn = __dadd_rn(tn, P.dt);
-        clk_out->sync_step = step + 1ull;
+        clk_out->sync_step = step + count_sync;
     }
     if (blockIdx.x < n_main) {
         const int lane = threadIdx.x & 31;
-        const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int64_t slice = slice_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         if (slice >= P.n_slices) return;
         double s[3];
-        saa_node_dot<SAA_UNROLL, true>(P, slice, lane, d0, s);
-        if (slice < P.sh_slices) {
+        saa_node_dot<MODE, true>(P, slice, lane, d0, s);
+        if (slice < P.sh_slices && !(H.dbg & 8)) {
 #pragma unroll
             for (int A = 0; A < 3; ++A) {
                 const int64_t row = 3 * (slice * 32 + lane) + A;
                 H.xbuf[row] = s[A];
                 for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
                     const int nb = H.dst_nb[k];
-                    H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
+                    if (H.dbg & 2) H.sendbuf[H.dst_pos[k] % 3] = s[A];
+                    else H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
                 }
             }
-            __threadfence_system();
+            if (!(H.dbg & 2)) __threadfence_system();
             __syncwarp();
             if (lane == 0) {
                 const unsigned int t = atomicAdd(H.done_ctr, 1u);
@@ -387,8 +452,11 @@ __global__ void __launch_bounds__(256) saa_k_step_fused(SaaDev P, SaaHaloDev H, 
         return;
     }
     // tail blocks: shared rows
-    if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
-    if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
+    if (H.dbg & 4) return;
+    if (!(H.dbg & 1)) {
+        if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
+        if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
+    }
     __syncthreads();
     const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
     const int64_t row = (int64_t)(blockIdx.x - n_main) * blockDim.x + threadIdx.x;
@@ -418,7 +486,7 @@ __global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, 
         const double ramp = saa_ramp(tn);
         for (int64_t slice = warp0; slice < P.n_slices; slice += nwarps) {
             double s[3];
-            saa_node_dot<SAA_UNROLL, false>(P, slice, lane, d0, s);
+            saa_node_dot<SAA_DOT_MODE, false>(P, slice, lane, d0, s);
             saa_finish_node<false>(P, slice, lane, s, d0, dn, ramp);
         }
         tn = __dadd_rn(tn, P.dt);
