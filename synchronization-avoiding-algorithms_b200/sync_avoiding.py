@@ -51,6 +51,7 @@ class SyncAvoidingRun:
         self.i_cri = self.n_p * self.n_s - 1                                   # Online_predictor.py:63
         self.block = self.n_f * self.n_s
         self.tables = [] if keep_tables else None
+        self.t_predict = 0.0                                                   # wall seconds spent in LSTM inference
         self._live = []                                                        # tables referenced by the plans
         cap = self.n_p * self.n_s + self.block
         for pl, d in zip(self.plans, self.dofs):
@@ -86,7 +87,12 @@ class SyncAvoidingRun:
                 self.stepper.step(n, _plan.MODE_SYNC)
                 self.i += n
                 continue
+            import time as _time
+            for pl in self.plans:
+                pl.synchronize()
+            _t0 = _time.perf_counter()
             tables = self._predict_tables()                                    # :280
+            self.t_predict += _time.perf_counter() - _t0
             if self.tables is not None:
                 self.tables.append([t.cpu().numpy() for t in tables])
             self._live = tables
