@@ -236,25 +236,53 @@ def gather_node_lists(local_nodes, size):
 
 
 # ---- one rank of a structured cantilever, end to end --------------------------------------------------------------
-def structured_rank_local(m, rank, size, device_index=0, length=25, E=E_DEFAULT, nu=NU_DEFAULT, rho=RHO_DEFAULT,
-                          fz=FZ_DEFAULT, gamma=GAMMA_DEFAULT):
-    """Phase 1 (no communication): slab mesh, local numbering, stiffness, partial mass / load, local dt."""
+def rank_local(cells_global, points_of, clamped_of, rank, size, device_index=0, E=E_DEFAULT, nu=NU_DEFAULT, rho=RHO_DEFAULT,
+               fz=FZ_DEFAULT, gamma=GAMMA_DEFAULT, n_global_nodes=0, n_global_elem=0):
+    """Phase 1 (no communication) for ANY tetrahedral mesh: `cells_global` (nE_loc,4) int64 device tensor with the
+    global node ids of this rank's elements in ascending element order (Local_ele_list order); points_of(ids) ->
+    (n,3) float64 device coordinates of the given global node ids; clamped_of(ids) -> bool device mask of clamped
+    nodes.  Produces local numbering, stiffness, partial mass / load, local dt, clamped DOFs."""
     import torch
-    dev = torch.device("cuda", device_index)
     lmd, mu = lame(E, nu)
-    nx, ny, nz = mesh.structured_beam_dims(m, length)
-    cells_g = structured_slab_cells(m, rank, size, length, device=dev)
-    local_nodes, cells_loc = local_numbering(cells_g)
-    del cells_g
-    pts = structured_points(m, local_nodes, length)
+    local_nodes, cells_loc = local_numbering(cells_global)
+    pts = points_of(local_nodes)
     K = assemble_stiffness(cells_loc, pts, lmd, mu, device_index)
     m_node, F = assemble_mass_load(cells_loc, pts, rho, fz, device_index)
     dt_loc = gamma * min_edge_meshsize(cells_loc, pts) / np.sqrt(E / rho / (1 - nu ** 2))     # Data_prepare.py:147
-    clamped = torch.nonzero(local_nodes < (ny + 1) * (nz + 1)).reshape(-1).cpu().numpy()       # face x = 0 (:127-144)
+    clamped = torch.nonzero(clamped_of(local_nodes)).reshape(-1).cpu().numpy()                 # (:127-144) ascending local position
     return dict(rank=rank, size=size, device_index=device_index, local_nodes=local_nodes, n_nodes=local_nodes.numel(),
                 n_elem=cells_loc.shape[0], K=K, m_node=m_node, F=F, dt_loc=float(dt_loc),
-                dirichlet=maps.node_to_dof(3, [0, 1, 2], clamped),
-                n_global_nodes=(nx + 1) * (ny + 1) * (nz + 1), n_global_elem=6 * nx * ny * nz)
+                dirichlet=maps.node_to_dof(3, [0, 1, 2], clamped), n_global_nodes=n_global_nodes, n_global_elem=n_global_elem)
+
+
+def structured_rank_local(m, rank, size, device_index=0, length=25, **kw):
+    """Phase 1 for the structured cantilever: x-slab `rank` of `size`, generated on the device."""
+    import torch
+    dev = torch.device("cuda", device_index)
+    nx, ny, nz = mesh.structured_beam_dims(m, length)
+    cells_g = structured_slab_cells(m, rank, size, length, device=dev)
+    return rank_local(cells_g, lambda ids: structured_points(m, ids, length), lambda ids: ids < (ny + 1) * (nz + 1), rank, size,
+                      device_index, n_global_nodes=(nx + 1) * (ny + 1) * (nz + 1), n_global_elem=6 * nx * ny * nz, **kw)
+
+
+def mesh_rank_local(points, cells, facets, epart, rank, size, device_index=0, **kw):
+    """Phase 1 for a mesh given as host arrays (meshio / gmsh output) and an element -> rank vector `epart`:
+    only this rank's elements and the coordinate table travel to the device."""
+    import torch
+    dev = torch.device("cuda", device_index)
+    cells = np.asarray(cells, dtype=np.int64)
+    ele = np.nonzero(np.asarray(epart) == rank)[0]
+    cells_g = torch.from_numpy(cells[ele]).to(dev)
+    P = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).to(dev)
+    is_clamped = torch.zeros(len(points), dtype=torch.bool, device=dev)
+    D = mesh.dirichlet_nodes(np.asarray(points), np.asarray(facets))                           # Data_prepare.py:127-135
+    if len(D):
+        is_clamped[torch.from_numpy(D).to(dev)] = True
+    return rank_local(cells_g, lambda ids: P[ids].contiguous(), lambda ids: is_clamped[ids], rank, size, device_index,
+                      n_global_nodes=len(points), n_global_elem=len(cells), **kw)
+
+
+rank_plan = None   # set below (generic name of structured_rank_plan)
 
 
 def shared_partials(loc, halo):
@@ -290,8 +318,18 @@ def structured_rank_plan(loc, halo, recv, dt, alpha=DAMP_DEFAULT, keep_csr=False
 
 def build_structured_rank(m, rank, size, device_index=0, alpha=DAMP_DEFAULT, keep_csr=False, **kw):
     """One process per GPU (collective over torch.distributed when size > 1): (StepPlan, info)."""
+    return finish_rank(structured_rank_local(m, rank, size, device_index, **kw), alpha, keep_csr)
+
+
+def build_mesh_rank(points, cells, facets, epart, rank, size, device_index=0, alpha=DAMP_DEFAULT, keep_csr=False, **kw):
+    """Same for an arbitrary tetrahedral mesh + partition vector (one process per GPU, collective when size > 1)."""
+    return finish_rank(mesh_rank_local(points, cells, facets, epart, rank, size, device_index, **kw), alpha, keep_csr)
+
+
+def finish_rank(loc, alpha=DAMP_DEFAULT, keep_csr=False):
+    """Phase 2 of a one-process-per-GPU build: interface description, rank-ordered mass / load sums, global dt, plan."""
     import torch
-    loc = structured_rank_local(m, rank, size, device_index, **kw)
+    rank, size = loc["rank"], loc["size"]
     halo, recv, dt = None, None, loc["dt_loc"]
     if size > 1:
         import torch.distributed as dist
@@ -309,7 +347,17 @@ def build_structured_rank(m, rank, size, device_index=0, alpha=DAMP_DEFAULT, kee
 def build_structured_in_process(m, size, device_index=0, alpha=DAMP_DEFAULT, keep_csr=False, **kw):
     """All ranks of the layer-slab partition in ONE process on one GPU (tests; P partitions on fewer GPUs):
     returns (plans, infos); wrap the plans in plan.PlanGroup to step them together."""
-    locs = [structured_rank_local(m, r, size, device_index, **kw) for r in range(size)]
+    return finish_in_process([structured_rank_local(m, r, size, device_index, **kw) for r in range(size)], alpha, keep_csr)
+
+
+def build_mesh_in_process(points, cells, facets, epart, size, device_index=0, alpha=DAMP_DEFAULT, keep_csr=False, **kw):
+    """All ranks of an arbitrary partitioned mesh in ONE process on one GPU: (plans, infos)."""
+    return finish_in_process([mesh_rank_local(points, cells, facets, epart, r, size, device_index, **kw) for r in range(size)],
+                             alpha, keep_csr)
+
+
+def finish_in_process(locs, alpha=DAMP_DEFAULT, keep_csr=False):
+    size = len(locs)
     lists = [l["local_nodes"].cpu().numpy() for l in locs]
     halos = [maps.halo_plan(r, size, lists) if size > 1 else None for r in range(size)]
     sends = [holders_send(halos[r], shared_partials(locs[r], halos[r])) if size > 1 else {} for r in range(size)]
@@ -319,3 +367,6 @@ def build_structured_in_process(m, size, device_index=0, alpha=DAMP_DEFAULT, kee
         recv = {nb: sends[nb][r] for nb in halos[r]["neighbours"]} if size > 1 else None
         out.append(structured_rank_plan(locs[r], halos[r], recv, dt, alpha, keep_csr))
     return [o[0] for o in out], [o[1] for o in out]
+
+
+rank_plan = structured_rank_plan
