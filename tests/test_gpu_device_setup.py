@@ -160,7 +160,7 @@ def test_device_setup_of_an_unstructured_partitioned_mesh(name):
         Kd = i["K"].to_scipy()
         diff = Kd - Kref
         assert (np.abs(diff.data).max() if diff.nnz else 0.0) <= 4e-15 * np.abs(Kref.data).max()
-        assert abs(Kd.nnz - Kref.nnz) <= 0.01 * Kref.nnz      # which mathematically-zero entries round to exactly 0.0 differs
+        assert abs(Kd.nnz - Kref.nnz) <= 0.05 * Kref.nnz      # which mathematically-zero entries round to exactly 0.0 differs
         F, lM = i["F"].cpu().numpy(), i["lM"].cpu().numpy()
         assert np.abs(lM - ref["lM"][:, 0]).max() <= 1e-15 * np.abs(ref["lM"]).max()
         assert np.abs(F - ref["F"][:, 0]).max() <= 1e-15 * np.abs(ref["F"]).max()
