@@ -6,10 +6,17 @@ Per the north star the surrogate stays plain PyTorch (cuDNN LSTM on the GPU).  W
 is `model_predict_batch`: the reference predicts the n_s interleaved "combs" of a refill block one by one with
 batch size 1 (DNN_prediction.py:43-54); they are independent, so they run here as ONE batch on the device.
 """
+import random
+
 import numpy as np
 import torch
 import torch.nn as nn
 from torch.utils.data import Dataset
+
+try:                                    # the reference's scripts reach `plt` through `from Tools.DNN_tools import *`
+    from matplotlib import pyplot as plt
+except Exception:                       # plotting is optional
+    plt = None
 
 
 class LSTM_Encoder(nn.Module):
@@ -80,6 +87,56 @@ def model_predict_batch(model, X, n_future):
 def model_predict(device, model, X, n_future):
     """Reference signature (DNN_tools.py:212-234): X (n_past, input) -> (n_future, input) tensor on `device`."""
     return model_predict_batch(model, X.unsqueeze(0).to(device), n_future)[0]
+
+
+def _decode(model, X, n_future, truth=None, ratio=0.0):
+    """encoder once, n_future recursive decoder steps; with `truth` and ratio > 0: mixed teacher forcing"""
+    h, c = model.encoder(X)
+    y = X[:, -1, :]
+    outs = []
+    for i in range(n_future):
+        y, h, c = model.decoder(y, h, c)
+        outs.append(y)
+        if truth is not None and random.random() < ratio:
+            y = truth[:, i, :]
+    return torch.stack(outs, dim=1)
+
+
+def _scores(criterion, out, truth):
+    """(mse, R2-type accuracy, relative accuracy) as the reference reports them (DNN_tools.py:146-155)"""
+    loss = criterion(out, truth)
+    r2 = 1.0 - loss / criterion(truth, torch.mean(truth) + torch.zeros_like(truth))
+    rel = 1.0 - loss / criterion(truth, torch.zeros_like(truth))
+    return loss, r2, rel
+
+
+def model_train(device, model, trainloader, criterion, optimizer, n_future, training_method='recursive', ratio=0.5):
+    """One epoch over `trainloader` (DNN_tools.py:103-165): returns (sum loss, sum R2, sum rel, model).
+    training_method 'recursive' feeds predictions back; 'mtf' mixes in the truth with probability `ratio`,
+    lowered by 0.005 per batch."""
+    tot = [0.0, 0.0, 0.0]
+    model.train()
+    for xb, yb in trainloader:
+        optimizer.zero_grad()
+        out = _decode(model, xb, n_future, yb if training_method == 'mtf' else None, ratio)
+        loss, r2, rel = _scores(criterion, out, yb)
+        tot[0] += loss.item(); tot[1] += r2.item(); tot[2] += rel.item()
+        loss.backward()
+        optimizer.step()
+        if ratio > 0.005:
+            ratio -= 0.005
+    return tot[0], tot[1], tot[2], model
+
+
+def model_test(device, model, testloader, criterion, n_future):
+    """Validation pass without gradients (DNN_tools.py:170-207): (sum loss, sum R2, sum rel)."""
+    tot = [0.0, 0.0, 0.0]
+    model.eval()
+    with torch.no_grad():
+        for xb, yb in testloader:
+            loss, r2, rel = _scores(criterion, _decode(model, xb, n_future), yb)
+            tot[0] += loss.item(); tot[1] += r2.item(); tot[2] += rel.item()
+    return tot[0], tot[1], tot[2]
 
 
 class MyDataset(Dataset):

@@ -185,3 +185,47 @@ def test_online_predictor_shaped_driver_two_processes(tmp_path):
         # synchronised warm-up against the golden history loosely and the two execution paths tightly
         assert got.shape == hist[k].shape
         assert np.abs(got - hist[k]).max() <= 1e-9 * max(np.abs(hist[k]).max(), 1e-30)
+
+
+def test_training_functions_reduce_the_loss():
+    """model_train / model_test (reference names) on a tiny synthetic history: a few epochs lower the MSE."""
+    import torch
+    from Tools.DNN_tools import (LSTM_encoder_decoder, MyDataset, Scale_to_zero_one, model_test, model_train, windows_from_history)
+    torch.manual_seed(0)
+    t = np.arange(600)[:, None] * 0.05
+    H = 1e-3 * np.sin(t + np.linspace(0, 1, 6)[None, :])
+    X, Y = windows_from_history(H, 6, 2, 5, 4, 1.0)
+    X, Y, smax, smin = Scale_to_zero_one(X, Y)
+    model = LSTM_encoder_decoder(6, 8, 2, True, 0.0, 0.0)
+    crit = torch.nn.MSELoss()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+    loader = torch.utils.data.DataLoader(MyDataset(X, Y), batch_size=16, shuffle=True)
+    first = model_test("cpu", model, loader, crit, 4)[0]
+    for _ in range(6):
+        model_train("cpu", model, loader, crit, opt, 4)
+    last, r2, rel = model_test("cpu", model, loader, crit, 4)
+    assert last < 0.5 * first
+
+
+@pytest.mark.reference
+def test_reference_shared_extraction_script_runs_unchanged_on_this_package(tmp_path):
+    """The reference's own Shared_extraction.py, byte for byte, executed through run_driver.py on top of the drop-in
+    `Tools` + compat stand-ins: it must pick exactly the shared-DOF rows (Shared_extraction.py:27-40)."""
+    import subprocess
+    g = load_golden("beam_coarse_P2")
+    for q, r in enumerate(g["ranks"]):
+        os.makedirs(tmp_path / "Results" / "Rankwised_Data", exist_ok=True)
+        os.makedirs(tmp_path / "Results" / "Shared_Data", exist_ok=True)
+        os.makedirs(tmp_path / "Results" / "Dynamics", exist_ok=True)
+        np.savetxt(str(tmp_path / "Results" / "Rankwised_Data" / f"Rank={q}_local_nodes.csv"), r["nodes"], delimiter=",", fmt="%d")
+        np.savetxt(str(tmp_path / "Results" / "Shared_Data" / f"Rank={q}_shared.csv"), r["shared"], delimiter=",", fmt="%d")
+    r0 = g["ranks"][0]
+    D = np.stack([g["hist_1_r0"], g["hist_10_r0"], g["hist_100_r0"]], axis=1)
+    np.savez_compressed(str(tmp_path / "Results" / "Dynamics" / "Local-rank-0.hdf5.npz"), Displacement=D)
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run([sys.executable, os.path.join(PKG, "run_driver.py"), "/root/reference/Shared_extraction.py"], cwd=str(tmp_path),
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = np.load(str(tmp_path / "Results" / "sol_on_shared" / "rank=0-shared_dof.hdf5.npz"))["Displacement"]
+    assert np.array_equal(out, D[r0["loc_dof_shared"], :])
