@@ -13,7 +13,7 @@ same numbers are produced without any dense matrix:
 * exact zeros are dropped and columns are ascending within a row, as csr_matrix(dense) does
   (Mat_construction.py:150); indices are int32 like scipy's.
 
-`tests/test_assembly.py` checks bit-equality with the reference's own output (in the authoring
+`tests/test_maps_assembly.py` checks bit-equality with the reference's own output (in the authoring
 container) and ulp-level agreement with the golden fixtures elsewhere.
 """
 from __future__ import annotations

@@ -56,3 +56,20 @@ def test_step_scalars_follow_python_expressions():
     dt = np.float64(0.00024784067462642383)
     s = splan.step_scalars(dt, 0.5)
     assert s == (float(dt), float(dt ** 2), float(dt / 2), 0.25, 0.5)
+
+
+def test_argument_errors_are_reported_before_any_device_work():
+    """Shape errors come back as status + message, whatever the machine (checked before the device is touched)."""
+    L = splan.lib()
+    h = ctypes.c_void_p()
+    ip = np.array([0, 1, 2, 3, 4], dtype=np.int32)
+    ix = np.zeros(4, dtype=np.int32)
+    dv = np.ones(4)
+    v = np.ones(4)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = L.saa_plan_create(ctypes.byref(h), 0, 4, p(ip), p(ix), p(dv), p(v), p(v), None, 0, 1e-3, 1e-6, 5e-4, 0.25, 0.5)
+    assert rc != 0 and b"multiple of 3" in L.saa_last_error()
+    rc = L.saa_plan_create(ctypes.byref(h), 0, 0, p(ip), p(ix), p(dv), p(v), p(v), None, 0, 1e-3, 1e-6, 5e-4, 0.25, 0.5)
+    assert rc != 0 and b"null or empty" in L.saa_last_error()
+    assert L.saa_plan_step(None, 1, 0, 0) != 0 and b"null plan" in L.saa_last_error()
+    assert L.saa_plan_destroy(None) == 0

@@ -259,3 +259,36 @@ def test_one_process_per_gpu_transports(transport, name, n):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(f"ok ({transport})") == n
+
+
+def test_malformed_matrices_are_rejected_and_plans_can_be_recycled():
+    import scipy.sparse as sp
+    g = load_golden("beam_coarse_P1")
+    r = g["ranks"][0]
+    n = r["F"].size
+    bad = r["K_indices"].copy()
+    a, b = r["K_indptr"][5], r["K_indptr"][6]
+    bad[a:b] = bad[a:b][::-1]                                # descending columns in one row
+    Kbad = sp.csr_matrix((r["K_data"], bad, r["K_indptr"]), shape=(n, n))
+    Kbad.has_sorted_indices = True                           # keep scipy from repairing it
+    with pytest.raises(splan.SaaError, match="sorted"):
+        splan.StepPlan(Kbad, r["F"], r["lM"], r["dirichlet"], g["dt"], 0.5)
+    with pytest.raises(splan.SaaError):
+        splan.StepPlan(sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n)), r["F"][:-3], r["lM"], r["dirichlet"], g["dt"], 0.5)
+    # create / step / destroy repeatedly: no state leaks from one plan into the next
+    ref = None
+    for _ in range(20):
+        pl = golden_plans_single(g, 0)
+        pl.step(50, splan.MODE_LOCAL)
+        pl.synchronize()
+        d = pl.d0()
+        pl.close()
+        assert ref is None or bits_equal(d, ref)
+        ref = d
+    assert bits_equal(ref, make_oracle(g).__class__ and _oracle_after(g, 50))
+
+
+def _oracle_after(g, n):
+    o = make_oracle(g)
+    o.run(n)
+    return o.d0(0)
