@@ -154,7 +154,7 @@ struct saa_plan {
     // execution
     cudaStream_t stream = nullptr;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // LOCAL-mode two-step graphs captured at cur = 0 / 1
-    int coop_blocks = 0;
+    int coop_blocks = 0, n_sms = 0;
     int64_t launches = 0;
     saa_ncclComm_t comm = nullptr;
     saa_group *group = nullptr;
@@ -470,6 +470,7 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, p->device));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, saa_k_persistent, 32 * SAA_WARPS_PER_BLOCK, 0));
     p->coop_blocks = dev_sms * occ;
+    p->n_sms = dev_sms;
 
     // host copies are no longer needed
     std::vector<int32_t>().swap(p->indptr); std::vector<int32_t>().swap(p->indices);
@@ -700,11 +701,26 @@ static void launch_step_kernel(int variant, unsigned grid, cudaStream_t st, cons
     default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
     }
 }
+#define SAA_STREAM_STAGES 4
+#define SAA_STREAM_WARPS 8
 // K1 only: slices [slice_begin, n_slices) as interior rows (no interface handling inside the kernel)
 static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, unsigned count_sync, bool advance_clock)
 {
     SaaDev D = p->D;
     D.sh_slices = 0;
+    if (p->kvariant == 6 && p->n_slices > slice_begin) {       // cp.async streaming kernel, persistent grid
+        const size_t smem = (size_t)SAA_STREAM_WARPS * SAA_STREAM_STAGES * SAA_STREAM_STAGE_BYTES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(saa_k_step_stream<SAA_STREAM_STAGES, SAA_STREAM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        saa_k_step_stream<SAA_STREAM_STAGES, SAA_STREAM_WARPS><<<p->n_sms, 32 * SAA_STREAM_WARPS, smem, st>>>(
+            D, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr,
+            slice_begin, count_sync);
+        p->launches++;
+        return;
+    }
     const unsigned n_main = std::max(1u, nblk(p->n_slices - slice_begin, SAA_WARPS_PER_BLOCK));
     launch_step_kernel(p->kvariant, n_main, st, D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
                        advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, n_main, count_sync);

@@ -470,6 +470,125 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
     saa_finish_row(P, row, Fi, d0, dn_d1, saa_ramp(tn));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streaming variant of K1 (schedule variant 6): the matrix reaches the SM through cp.async (L2 -> shared memory,
+// no registers, no L1), so the number of bytes in flight no longer depends on how ptxas schedules the loads.
+// The grid is persistent (one CTA per SM); every warp owns a CONTIGUOUS range of slices holding an equal share
+// of the block-lanes, i.e. one contiguous stream of the value / id arrays, which it pulls through a ring of
+// STAGES buffers of two block-rows (2 x (2304 B values + 128 B ids)) each.  The d0 gathers of a stage are issued
+// one stage ahead.  Same arithmetic in the same order as saa_node_dot / saa_finish_node — same bits.
+#define SAA_STREAM_STAGE_BYTES (2 * 2304 + 2 * 128)
+__device__ __forceinline__ void saa_cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void saa_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int STAGES, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, const double *__restrict__ d0, double *__restrict__ dn_d1,
+                                                                const SaaClock *clk_in, SaaClock *clk_out, int64_t slice_begin,
+                                                                unsigned int count_sync)
+{
+    extern __shared__ __align__(16) unsigned char saa_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double tn = clk_in->tn;
+    if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        clk_out->tn = __dadd_rn(tn, P.dt);
+        clk_out->sync_step = clk_in->sync_step + count_sync;
+    }
+    const double ramp = saa_ramp(tn);
+    // ---- this warp's contiguous range of slices: equal shares of the block-rows (a block-row = 32 block-lanes)
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, GW = (int64_t)gridDim.x * WARPS;
+    const int64_t base = P.slice_ptr[slice_begin] >> 5, total = (P.slice_ptr[P.n_slices] >> 5) - base;
+    auto first_slice_at = [&](int64_t brow) {          // first slice s >= slice_begin with slice_ptr[s]/32 >= brow
+        int64_t lo = slice_begin, hi = P.n_slices;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((P.slice_ptr[mid] >> 5) < brow) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    // slices are split where their first block-row crosses the share boundary; zero-length slices go with their successor's owner
+    int64_t sa = (gw == 0) ? slice_begin : first_slice_at(base + (total * gw + GW - 1) / GW);
+    int64_t sb = (gw == GW - 1) ? P.n_slices : first_slice_at(base + (total * (gw + 1) + GW - 1) / GW);
+    if (gw != 0) { while (sa > slice_begin && P.slice_ptr[sa - 1] == P.slice_ptr[sa]) --sa; }       // leading empty slices belong here ...
+    if (gw != GW - 1) { while (sb > sa && sb > slice_begin && P.slice_ptr[sb - 1] == P.slice_ptr[sb]) --sb; }   // ... so trailing ones do not
+    if (sa >= sb) return;
+    const int64_t br0 = P.slice_ptr[sa] >> 5, br1 = P.slice_ptr[sb] >> 5;
+    const int64_t n_stage = (br1 - br0 + 1) >> 1;
+    unsigned char *ring = saa_smem + (size_t)warp * STAGES * SAA_STREAM_STAGE_BYTES;
+
+    auto issue = [&](int64_t k) {                      // stage k -> buffer k % STAGES (an empty group past the end)
+        if (k < n_stage) {
+            const int64_t br = br0 + 2 * k;
+            const int nbr = (int)((br1 - br) < 2 ? (br1 - br) : 2);
+            unsigned char *buf = ring + (size_t)(k % STAGES) * SAA_STREAM_STAGE_BYTES;
+            const unsigned char *gv = (const unsigned char *)(P.val + 288 * br);       // 9 planes x 32 lanes per block-row
+            const unsigned char *gc = (const unsigned char *)(P.col + 32 * br);
+            for (int ch = lane; ch < 144 * nbr; ch += 32) saa_cp_async16(buf + 16 * ch, gv + 16 * ch);
+            for (int ch = lane; ch < 8 * nbr; ch += 32) saa_cp_async16(buf + 4608 + 16 * ch, gc + 16 * ch);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto gather = [&](int64_t k, double (&x)[2][3]) {  // d0 components of the column nodes of stage k (already in shared memory)
+        const unsigned char *buf = ring + (size_t)(k % STAGES) * SAA_STREAM_STAGE_BYTES;
+        const int32_t *sc = (const int32_t *)(buf + 4608);
+        const int64_t br = br0 + 2 * k;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (br + j < br1) {
+                const double *xp = d0 + 3 * (int64_t)sc[32 * j + lane];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) x[j][b] = __ldg(xp + b);
+            }
+    };
+
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; ++k) issue(k);
+    saa_cp_async_wait<STAGES - 2>();                   // stage 0 has landed
+    __syncwarp();
+    double xc[2][3], xn[2][3];
+    gather(0, xc);
+    int64_t cs = sa;                                   // current slice and the block-rows it still expects
+    int64_t rem = (P.slice_ptr[cs + 1] - P.slice_ptr[cs]) >> 5;
+    double s[3] = {0.0, 0.0, 0.0};
+    auto close_finished_slices = [&]() {               // finish every slice whose rows are complete (also empty ones)
+        while (rem == 0 && cs < sb) {
+            saa_finish_node<true>(P, cs, lane, s, d0, dn_d1, ramp);
+            s[0] = 0.0; s[1] = 0.0; s[2] = 0.0;
+            ++cs;
+            if (cs < sb) rem = (P.slice_ptr[cs + 1] - P.slice_ptr[cs]) >> 5;
+        }
+    };
+    close_finished_slices();
+    for (int64_t k = 0; k < n_stage; ++k) {
+        issue(k + STAGES - 1);                         // refills the buffer consumed in the previous iteration
+        saa_cp_async_wait<STAGES - 2>();               // stages <= k + 1 have landed
+        __syncwarp();
+        if (k + 1 < n_stage) gather(k + 1, xn);
+        const unsigned char *buf = ring + (size_t)(k % STAGES) * SAA_STREAM_STAGE_BYTES;
+        const double *sv = (const double *)buf;
+        const int64_t br = br0 + 2 * k;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (br + j < br1) {
+                double a[9];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) a[e] = sv[(9 * j + e) * 32 + lane];
+                saa_block_madd(a, xc[j], s);
+                --rem;
+                close_finished_slices();
+            }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) xc[j][b] = xn[j][b];
+        __syncwarp();                                  // every lane is done with this buffer before it is refilled
+    }
+    saa_cp_async_wait<0>();
+}
+
 // Persistent variant of K1 (local mode): one cooperative launch runs n_steps time steps; u stays in HBM/L2,
 // the two displacement buffers swap roles after each grid-wide barrier.  tn advances in registers with the
 // same sequence of additions as the host loop (Data_prepare.py:235).
