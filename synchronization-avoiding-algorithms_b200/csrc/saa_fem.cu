@@ -701,24 +701,26 @@ static void launch_step_kernel(int variant, unsigned grid, cudaStream_t st, cons
     default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
     }
 }
-#define SAA_STREAM_STAGES 4
-#define SAA_STREAM_WARPS 8
+template <int STAGES, int WARPS, int BR>
+static void launch_stream(saa_plan *p, cudaStream_t st, const SaaDev &D, int64_t slice_begin, unsigned count_sync, bool advance_clock)
+{
+    const size_t smem = (size_t)WARPS * STAGES * SAA_STREAM_STAGE_BYTES(BR);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(saa_k_step_stream<STAGES, WARPS, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    saa_k_step_stream<STAGES, WARPS, BR><<<p->n_sms, 32 * WARPS, smem, st>>>(D, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
+                                                                       advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, count_sync);
+    p->launches++;
+}
 // K1 only: slices [slice_begin, n_slices) as interior rows (no interface handling inside the kernel)
 static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, unsigned count_sync, bool advance_clock)
 {
     SaaDev D = p->D;
     D.sh_slices = 0;
-    if (p->kvariant == 6 && p->n_slices > slice_begin) {       // cp.async streaming kernel, persistent grid
-        const size_t smem = (size_t)SAA_STREAM_WARPS * SAA_STREAM_STAGES * SAA_STREAM_STAGE_BYTES;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(saa_k_step_stream<SAA_STREAM_STAGES, SAA_STREAM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
-        saa_k_step_stream<SAA_STREAM_STAGES, SAA_STREAM_WARPS><<<p->n_sms, 32 * SAA_STREAM_WARPS, smem, st>>>(
-            D, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr,
-            slice_begin, count_sync);
-        p->launches++;
+    if (p->kvariant >= 6 && p->n_slices > slice_begin) {       // cp.async streaming kernels, persistent grid
+        launch_stream<3, 24, 1>(p, st, D, slice_begin, count_sync, advance_clock);   // the fastest streaming configuration measured
         return;
     }
     const unsigned n_main = std::max(1u, nblk(p->n_slices - slice_begin, SAA_WARPS_PER_BLOCK));

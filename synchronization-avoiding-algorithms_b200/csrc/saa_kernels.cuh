@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
 // of the block-lanes, i.e. one contiguous stream of the value / id arrays, which it pulls through a ring of
 // STAGES buffers of two block-rows (2 x (2304 B values + 128 B ids)) each.  The d0 gathers of a stage are issued
 // one stage ahead.  Same arithmetic in the same order as saa_node_dot / saa_finish_node — same bits.
-#define SAA_STREAM_STAGE_BYTES (2 * 2304 + 2 * 128)
+#define SAA_STREAM_STAGE_BYTES(BR) ((BR) * (2304 + 128))
 __device__ __forceinline__ void saa_cp_async16(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -485,7 +485,7 @@ __device__ __forceinline__ void saa_cp_async16(void *smem_dst, const void *gmem_
 template <int N>
 __device__ __forceinline__ void saa_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int STAGES, int WARPS>
+template <int STAGES, int WARPS, int BR>
 __global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, const double *__restrict__ d0, double *__restrict__ dn_d1,
                                                                 const SaaClock *clk_in, SaaClock *clk_out, int64_t slice_begin,
                                                                 unsigned int count_sync)
@@ -516,27 +516,28 @@ __global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, con
     if (gw != GW - 1) { while (sb > sa && sb > slice_begin && P.slice_ptr[sb - 1] == P.slice_ptr[sb]) --sb; }   // ... so trailing ones do not
     if (sa >= sb) return;
     const int64_t br0 = P.slice_ptr[sa] >> 5, br1 = P.slice_ptr[sb] >> 5;
-    const int64_t n_stage = (br1 - br0 + 1) >> 1;
-    unsigned char *ring = saa_smem + (size_t)warp * STAGES * SAA_STREAM_STAGE_BYTES;
+    const int64_t n_stage = (br1 - br0 + BR - 1) / BR;
+    constexpr int SB = SAA_STREAM_STAGE_BYTES(BR);
+    unsigned char *ring = saa_smem + (size_t)warp * STAGES * SB;
 
     auto issue = [&](int64_t k) {                      // stage k -> buffer k % STAGES (an empty group past the end)
         if (k < n_stage) {
-            const int64_t br = br0 + 2 * k;
-            const int nbr = (int)((br1 - br) < 2 ? (br1 - br) : 2);
-            unsigned char *buf = ring + (size_t)(k % STAGES) * SAA_STREAM_STAGE_BYTES;
+            const int64_t br = br0 + BR * k;
+            const int nbr = (int)((br1 - br) < BR ? (br1 - br) : BR);
+            unsigned char *buf = ring + (size_t)(k % STAGES) * SB;
             const unsigned char *gv = (const unsigned char *)(P.val + 288 * br);       // 9 planes x 32 lanes per block-row
             const unsigned char *gc = (const unsigned char *)(P.col + 32 * br);
             for (int ch = lane; ch < 144 * nbr; ch += 32) saa_cp_async16(buf + 16 * ch, gv + 16 * ch);
-            for (int ch = lane; ch < 8 * nbr; ch += 32) saa_cp_async16(buf + 4608 + 16 * ch, gc + 16 * ch);
+            for (int ch = lane; ch < 8 * nbr; ch += 32) saa_cp_async16(buf + 2304 * BR + 16 * ch, gc + 16 * ch);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto gather = [&](int64_t k, double (&x)[2][3]) {  // d0 components of the column nodes of stage k (already in shared memory)
-        const unsigned char *buf = ring + (size_t)(k % STAGES) * SAA_STREAM_STAGE_BYTES;
-        const int32_t *sc = (const int32_t *)(buf + 4608);
-        const int64_t br = br0 + 2 * k;
+    auto gather = [&](int64_t k, double (&x)[BR][3]) {  // d0 components of the column nodes of stage k (already in shared memory)
+        const unsigned char *buf = ring + (size_t)(k % STAGES) * SB;
+        const int32_t *sc = (const int32_t *)(buf + 2304 * BR);
+        const int64_t br = br0 + BR * k;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < BR; ++j)
             if (br + j < br1) {
                 const double *xp = d0 + 3 * (int64_t)sc[32 * j + lane];
 #pragma unroll
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, con
     for (int k = 0; k < STAGES - 1; ++k) issue(k);
     saa_cp_async_wait<STAGES - 2>();                   // stage 0 has landed
     __syncwarp();
-    double xc[2][3], xn[2][3];
+    double xc[BR][3], xn[BR][3];
     gather(0, xc);
     int64_t cs = sa;                                   // current slice and the block-rows it still expects
     int64_t rem = (P.slice_ptr[cs + 1] - P.slice_ptr[cs]) >> 5;
@@ -567,11 +568,11 @@ __global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, con
         saa_cp_async_wait<STAGES - 2>();               // stages <= k + 1 have landed
         __syncwarp();
         if (k + 1 < n_stage) gather(k + 1, xn);
-        const unsigned char *buf = ring + (size_t)(k % STAGES) * SAA_STREAM_STAGE_BYTES;
+        const unsigned char *buf = ring + (size_t)(k % STAGES) * SB;
         const double *sv = (const double *)buf;
-        const int64_t br = br0 + 2 * k;
+        const int64_t br = br0 + BR * k;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < BR; ++j)
             if (br + j < br1) {
                 double a[9];
 #pragma unroll
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, con
                 close_finished_slices();
             }
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < BR; ++j)
 #pragma unroll
             for (int b = 0; b < 3; ++b) xc[j][b] = xn[j][b];
         __syncwarp();                                  // every lane is done with this buffer before it is refilled
