@@ -104,14 +104,15 @@ __device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsign
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// bounded spin (about two seconds): a peer that never delivers must not hang the GPU
+// bounded spin (about 30 s at 1.9 GHz — ranks may legitimately be seconds apart, e.g. around file output or the first
+// cuDNN call of the surrogate): a peer that never delivers must not hang the GPU for good
 template <bool SYS>
 __device__ __forceinline__ void saa_wait_ge(const unsigned long long *flag, unsigned long long target, unsigned int *err)
 {
     const long long t0 = clock64();
     while ((SYS ? ld_acquire_sys_u64(flag) : ld_acquire_gpu_u64(flag)) < target) {
         __nanosleep(100);
-        if (clock64() - t0 > (1ll << 32)) { *err = 1u; break; }
+        if (clock64() - t0 > 60000000000ll) { *err = 1u; break; }
     }
 }
 
