@@ -20,6 +20,8 @@ def _plan_for(LocalK, F_rankwise, Local_nodes, Local_Dirichlet, T, l_M, alpha, s
     hit = _plans.get(key)
     if hit is not None and hit[0]() is LocalK and hit[2] == (float(T.dt), float(alpha), size, rank):
         return hit[1]
+    for k in [k for k, v in _plans.items() if v[0]() is None]:      # matrices that no longer exist: release their plans
+        _plans.pop(k)[1].close()
     halo = None
     if size != 1:
         nodes = np.asarray(Local_nodes, dtype=np.int64)

@@ -705,11 +705,7 @@ template <int STAGES, int WARPS, int BR>
 static void launch_stream(saa_plan *p, cudaStream_t st, const SaaDev &D, int64_t slice_begin, unsigned count_sync, bool advance_clock)
 {
     const size_t smem = (size_t)WARPS * STAGES * SAA_STREAM_STAGE_BYTES(BR);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(saa_k_step_stream<STAGES, WARPS, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(saa_k_step_stream<STAGES, WARPS, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
     saa_k_step_stream<STAGES, WARPS, BR><<<p->n_sms, 32 * WARPS, smem, st>>>(D, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
                                                                        advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, count_sync);
     p->launches++;
