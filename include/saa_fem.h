@@ -123,6 +123,15 @@ int saa_device_free(void *ptr);
 /* cudaMemcpy(dst, src, bytes, cudaMemcpyDefault) — lets bindings read the arrays above */
 int saa_device_copy(void *dst, const void *src, int64_t bytes);
 
+/*
+ * Optional, before saa_plan_finalize: the order in which the (non-interface) nodes are laid out in HBM — a
+ * permutation of 0 .. n_dof/3-1, e.g. a space-filling-curve or reverse Cuthill-McKee order.  It only changes where
+ * rows live (gather locality); results are bit-identical, external numbering is untouched.  Default: ascending
+ * local node id, i.e. the reference's first-appearance order (Distributed_tools.py:14-24), which is as coherent
+ * as the element order of the mesh file.
+ */
+int saa_plan_set_node_order(saa_plan *plan, const int32_t *order_host, int64_t n_nodes);
+
 /* Upload everything to the GPU (boundary-first row order, sliced-ELL storage). */
 int saa_plan_finalize(saa_plan *plan);
 int saa_plan_destroy(saa_plan *plan);

@@ -203,8 +203,16 @@ static int finalize_device(saa_plan *p)
         saa_k_fin_flag<<<nblk(n_sh, 256), 256>>>(n_sh, sh_nodes, flag);
     }
     int32_t *in_nodes = b_in.as<int32_t>();
-    const int64_t n_in = thrust::copy_if(thrust::device, thrust::counting_iterator<int32_t>(0), thrust::counting_iterator<int32_t>((int32_t)nn),
-                                         in_nodes, SaaIsZeroFlag{flag}) - in_nodes;
+    int64_t n_in = 0;
+    if (p->node_order.empty()) {
+        n_in = thrust::copy_if(thrust::device, thrust::counting_iterator<int32_t>(0), thrust::counting_iterator<int32_t>((int32_t)nn),
+                               in_nodes, SaaIsZeroFlag{flag}) - in_nodes;
+    } else {                                           // caller's locality-preserving order, interface nodes filtered out
+        DevBuf b_ord;
+        if (b_ord.alloc(nn * sizeof(int32_t))) return -1;
+        CK(cudaMemcpy(b_ord.p, p->node_order.data(), nn * sizeof(int32_t), cudaMemcpyHostToDevice));
+        n_in = thrust::copy_if(thrust::device, b_ord.as<int32_t>(), b_ord.as<int32_t>() + nn, in_nodes, SaaIsZeroFlag{flag}) - in_nodes;
+    }
     if (n_in != nn - n_sh) return fail("saa_plan_finalize: internal error (interior nodes %lld != %lld)", (long long)n_in, (long long)(nn - n_sh));
 
     // 2. sigma sort of both regions (stable: ties keep their order, like the host path)

@@ -110,6 +110,7 @@ struct saa_plan {
     // layout
     int64_t nnz = 0, padded_entries = 0, n_rows = 0, n_slices = 0, sh_slices = 0;
     std::vector<int32_t> iperm_h;          // external local DOF -> internal row
+    std::vector<int32_t> node_order;       // optional base order of the nodes (saa_plan_set_node_order); empty = ascending
     // device
     SaaDev D{};
     SaaHaloDev H{};
@@ -241,6 +242,20 @@ extern "C" int saa_plan_set_halo(saa_plan *p, int rank, int size, int64_t n_shar
     return 0;
 }
 
+extern "C" int saa_plan_set_node_order(saa_plan *p, const int32_t *order, int64_t n_nodes)
+{
+    if (!p) return fail("saa_plan_set_node_order: null plan");
+    if (p->finalized) return fail("saa_plan_set_node_order: plan already finalized");
+    if (!order || n_nodes != p->n_dof / 3) return fail("saa_plan_set_node_order: need one entry per node (%lld)", (long long)(p->n_dof / 3));
+    std::vector<char> seen(n_nodes, 0);
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (order[i] < 0 || order[i] >= n_nodes || seen[order[i]]) return fail("saa_plan_set_node_order: not a permutation of the nodes");
+        seen[order[i]] = 1;
+    }
+    p->node_order.assign(order, order + n_nodes);
+    return 0;
+}
+
 template <class T>
 static int upload(T **dptr, const std::vector<T> &h)
 {
@@ -307,8 +322,10 @@ extern "C" int saa_plan_finalize(saa_plan *p)
         sh_nodes.push_back(e);
     }
     in_nodes.reserve(nn - sh_nodes.size());
-    for (int64_t e = 0; e < nn; ++e)
+    for (int64_t i = 0; i < nn; ++i) {
+        const int64_t e = p->node_order.empty() ? i : p->node_order[i];     // caller's locality-preserving order, if any
         if (!is_shared[e]) in_nodes.push_back(e);
+    }
     sigma_sort(sh_nodes, nblk);
     sigma_sort(in_nodes, nblk);
     auto pad32 = [](int64_t v) { return (v + 31) / 32 * 32; };

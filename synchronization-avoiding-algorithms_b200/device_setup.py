@@ -237,7 +237,7 @@ def gather_node_lists(local_nodes, size):
 
 # ---- one rank of a structured cantilever, end to end --------------------------------------------------------------
 def rank_local(cells_global, points_of, clamped_of, rank, size, device_index=0, E=E_DEFAULT, nu=NU_DEFAULT, rho=RHO_DEFAULT,
-               fz=FZ_DEFAULT, gamma=GAMMA_DEFAULT, n_global_nodes=0, n_global_elem=0):
+               fz=FZ_DEFAULT, gamma=GAMMA_DEFAULT, n_global_nodes=0, n_global_elem=0, reorder=None):
     """Phase 1 (no communication) for ANY tetrahedral mesh: `cells_global` (nE_loc,4) int64 device tensor with the
     global node ids of this rank's elements in ascending element order (Local_ele_list order); points_of(ids) ->
     (n,3) float64 device coordinates of the given global node ids; clamped_of(ids) -> bool device mask of clamped
@@ -250,7 +250,8 @@ def rank_local(cells_global, points_of, clamped_of, rank, size, device_index=0, 
     m_node, F = assemble_mass_load(cells_loc, pts, rho, fz, device_index)
     dt_loc = gamma * min_edge_meshsize(cells_loc, pts) / np.sqrt(E / rho / (1 - nu ** 2))     # Data_prepare.py:147
     clamped = torch.nonzero(clamped_of(local_nodes)).reshape(-1).cpu().numpy()                 # (:127-144) ascending local position
-    return dict(rank=rank, size=size, device_index=device_index, local_nodes=local_nodes, n_nodes=local_nodes.numel(),
+    node_order = morton_node_order(pts) if reorder == "morton" else None
+    return dict(node_order=node_order, rank=rank, size=size, device_index=device_index, local_nodes=local_nodes, n_nodes=local_nodes.numel(),
                 n_elem=cells_loc.shape[0], K=K, m_node=m_node, F=F, dt_loc=float(dt_loc),
                 dirichlet=maps.node_to_dof(3, [0, 1, 2], clamped), n_global_nodes=n_global_nodes, n_global_elem=n_global_elem)
 
@@ -292,6 +293,24 @@ def shared_partials(loc, halo):
     return torch.cat([loc["m_node"][sp, None], loc["F"].view(-1, 3)[sp]], dim=1)
 
 
+def morton_node_order(pts):
+    """Z-order (Morton) permutation of the local nodes from their coordinates: nodes close in space end up close in
+    HBM whatever the element order of the mesh file was.  21 bits per axis."""
+    import torch
+    lo, hi = pts.min(0).values, pts.max(0).values
+    q = ((pts - lo) / torch.clamp(hi - lo, min=1e-300) * (2 ** 21 - 1)).long().clamp_(0, 2 ** 21 - 1)
+
+    def spread(v):                                          # insert two zero bits between the bits of v
+        v = (v | (v << 32)) & 0x1F00000000FFFF
+        v = (v | (v << 16)) & 0x1F0000FF0000FF
+        v = (v | (v << 8)) & 0x100F00F00F00F00F
+        v = (v | (v << 4)) & 0x10C30C30C30C30C3
+        v = (v | (v << 2)) & 0x1249249249249249
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return torch.argsort(code, stable=True).to(torch.int32).cpu().numpy()
+
+
 def structured_rank_plan(loc, halo, recv, dt, alpha=DAMP_DEFAULT, keep_csr=False):
     """Phase 2: fold the neighbours' partial mass / load in (rank-ordered sums), build the device plan."""
     import torch
@@ -306,7 +325,7 @@ def structured_rank_plan(loc, halo, recv, dt, alpha=DAMP_DEFAULT, keep_csr=False
     K = loc["K"]
     pl = StepPlan.from_device(3 * loc["n_nodes"], K.indptr, K.indices, K.data, loc["F"].data_ptr(), lM.data_ptr(),
                               loc["dirichlet"], dt, alpha, device=loc["device_index"], halo=halo if size > 1 else None,
-                              rank=rank, size=size)
+                              rank=rank, size=size, node_order=loc.get("node_order"))
     info = dict(n_nodes=loc["n_nodes"], n_elem=loc["n_elem"], nnz=K.nnz, dt=dt, local_nodes=loc["local_nodes"], halo=halo,
                 n_global_nodes=loc["n_global_nodes"], n_global_elem=loc["n_global_elem"])
     if keep_csr:

@@ -38,6 +38,7 @@ ABI = {
     "saa_device_free": (_int, [_vp]),
     "saa_device_copy": (_int, [_vp, _vp, _i64]),
     "saa_plan_set_halo": (_int, [_vp, _int, _int, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "saa_plan_set_node_order": (_int, [_vp, _vp, _i64]),
     "saa_plan_finalize": (_int, [_vp]),
     "saa_plan_destroy": (_int, [_vp]),
     "saa_plan_n_dof": (_i64, [_vp]),
@@ -120,6 +121,16 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def rcm_node_order(K):
+    """Reverse Cuthill-McKee order of the node graph of a 3-DOF-per-node CSR matrix (memory-layout hint)."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    n = K.shape[0] // 3
+    rows = np.repeat(np.arange(K.shape[0]), np.diff(K.indptr)) // 3
+    G = csr_matrix((np.ones(K.indices.size, dtype=np.int8), (rows, K.indices // 3)), shape=(n, n))
+    return reverse_cuthill_mckee(G.tocsr(), symmetric_mode=True).astype(np.int32)
+
+
 def step_scalars(dt, alpha):
     """Scalar sub-expressions of Dynamic_solver.py:17 with the reference's own Python expressions on the
     reference's own types (dt: np.float64, so `dt**2` is numpy's power; alpha: Python float)."""
@@ -130,9 +141,11 @@ def step_scalars(dt, alpha):
 class StepPlan:
     """Device-resident problem + state of one partition (one reference MPI rank)."""
 
-    def __init__(self, LocalK, F_rankwise, l_M, Local_Dirichlet, dt, alpha, device=0, halo=None, rank=0, size=1):
+    def __init__(self, LocalK, F_rankwise, l_M, Local_Dirichlet, dt, alpha, device=0, halo=None, rank=0, size=1, node_order=None):
         """LocalK: scipy CSR (sorted indices; its stored order is the summation order).
-        halo: dict from maps.halo_plan(rank, size, rank_nodal_list) when size > 1."""
+        halo: dict from maps.halo_plan(rank, size, rank_nodal_list) when size > 1.
+        node_order: optional permutation of the local nodes (memory layout only, see saa_plan_set_node_order);
+        "rcm" computes a reverse Cuthill-McKee order of the node graph here."""
         L = lib()
         K = LocalK.tocsr() if not hasattr(LocalK, "indptr") else LocalK
         n = K.shape[0]
@@ -153,12 +166,14 @@ class StepPlan:
                                  _p(F), _p(M), _p(D), D.size, self.dt, self.dt2, self.dt_half, self.half_alpha,
                                  self.alpha), "saa_plan_create")
         self.h = h
-        self._set_halo_and_finalize(halo)
+        if isinstance(node_order, str) and node_order == "rcm":
+            node_order = rcm_node_order(K)
+        self._set_halo_and_finalize(halo, node_order)
         del self._indptr, self._indices, self._data
 
     @classmethod
     def from_device(cls, n_dof, indptr_ptr, indices_ptr, data_ptr, F_ptr, lM_ptr, Local_Dirichlet, dt, alpha, device=0,
-                    halo=None, rank=0, size=1):
+                    halo=None, rank=0, size=1, node_order=None):
         """Plan from a CSR that already lives on the GPU (raw device pointers; int64 indptr, int32 indices)."""
         self = cls.__new__(cls)
         D = np.ascontiguousarray(Local_Dirichlet, dtype=np.int64).reshape(-1)
@@ -169,12 +184,15 @@ class StepPlan:
                                          _p(D), D.size, self.dt, self.dt2, self.dt_half, self.half_alpha, self.alpha),
                "saa_plan_create_dev")
         self.h = h
-        self._set_halo_and_finalize(halo)
+        self._set_halo_and_finalize(halo, node_order)
         return self
 
-    def _set_halo_and_finalize(self, halo):
+    def _set_halo_and_finalize(self, halo, node_order=None):
         L, h, rank, size = lib(), self.h, self.rank, self.size
         self._halo_desc = halo
+        if node_order is not None:
+            o = np.ascontiguousarray(node_order, dtype=np.int32).reshape(-1)
+            _check(L.saa_plan_set_node_order(h, _p(o), o.size), "saa_plan_set_node_order")
         if size > 1:
             if halo is None:
                 raise SaaError("size > 1 needs the halo description (maps.halo_plan)")

@@ -292,3 +292,33 @@ def _oracle_after(g, n):
     o = make_oracle(g)
     o.run(n)
     return o.d0(0)
+
+
+@pytest.mark.parametrize("name", ["beam_coarse_P1", "beam_coarse_P3"])
+@pytest.mark.parametrize("order", ["rcm", "random"])
+def test_node_order_hint_changes_layout_not_results(name, order):
+    """saa_plan_set_node_order moves rows around in HBM (gather locality); the histories stay bit-identical."""
+    import scipy.sparse as sp
+    g = load_golden(name)
+    P = g["P"]
+    lists = [r["nodes"] for r in g["ranks"]]
+    rng = np.random.default_rng(4)
+    plans = []
+    for q, r in enumerate(g["ranks"]):
+        n = r["F"].size
+        K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+        no = "rcm" if order == "rcm" else rng.permutation(n // 3)
+        plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), rank=q, size=P,
+                                    halo=maps.halo_plan(q, P, lists) if P > 1 else None, node_order=no))
+    grp = splan.PlanGroup(plans) if P > 1 else None
+    done = 0
+    for n in [int(s) for s in g["steps"]][:5]:
+        run(plans, grp, n - done, splan.MODE_SYNC)
+        done = n
+        for q in range(P):
+            assert bits_equal(plans[q].d0(), g[f"hist_{n}_r{q}"]), (name, order, n, q)
+    with pytest.raises(splan.SaaError, match="permutation"):
+        r = g["ranks"][0]
+        n = r["F"].size
+        K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+        splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], 0.5, node_order=np.zeros(n // 3, dtype=np.int32))
