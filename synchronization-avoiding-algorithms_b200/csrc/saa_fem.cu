@@ -152,6 +152,11 @@ struct saa_plan {
     int32_t *d_pred_rows = nullptr;
     const double *d_pred_table = nullptr;
     int64_t pred_n = 0, pred_rows = 0, pred_next = 0;
+    SaaHookDev hook_h{};                    // host mirror of the device-resident hook state
+    SaaHookDev *d_hook = nullptr;
+    int64_t hook_epoch = 0;                 // bumped when the hook configuration (not just the table) changes
+    struct StepGraph { int mode, cur; int64_t epoch; cudaGraphExec_t exec; int launches; };
+    std::vector<StepGraph> step_graphs;     // two-step graphs of steps with hooks
     // execution
     cudaStream_t stream = nullptr;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // LOCAL-mode two-step graphs captured at cur = 0 / 1
@@ -411,6 +416,9 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     }
     CK(cudaMalloc((void **)&p->d_clk, 2 * sizeof(SaaClock)));
     CK(cudaMemset(p->d_clk, 0, 2 * sizeof(SaaClock)));
+    CK(cudaMalloc((void **)&p->d_hook, sizeof(SaaHookDev)));
+    p->hook_h.hist_every = 1; p->hook_h.hist_cap = 1;
+    CK(cudaMemcpy(p->d_hook, &p->hook_h, sizeof(SaaHookDev), cudaMemcpyHostToDevice));
     CK(cudaMalloc((void **)&p->d_stage, 3 * n * sizeof(double)));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
 
@@ -512,10 +520,11 @@ extern "C" int saa_plan_destroy(saa_plan *p)
             if (p->graph_peer[i]) cudaGraphExecDestroy(p->graph_peer[i]);
         }
         for (void *m : p->peer_mapped) cudaIpcCloseMemHandle(m);
+        for (auto &g : p->step_graphs) cudaGraphExecDestroy(g.exec);
         void *ptrs[] = {p->d_slice_ptr, p->d_val, p->d_col, p->d_M, p->d_F, p->d_dir, p->d_iperm, p->d_buf[0], p->d_buf[1],
                         p->d_clk, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
                         p->d_recv, p->d_done, p->d_own_ready, p->d_dst_nb, p->d_dst_pos_peer, p->d_peer_recv, p->d_peer_stride, p->d_peer_flag,
-                        p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force};
+                        p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force, p->d_hook};
         for (void *q : ptrs)
             if (q) cudaFree(q);
         if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
@@ -618,6 +627,7 @@ extern "C" int saa_plan_set_history(saa_plan *p, const int64_t *dofs, int64_t n_
     if (p->d_hist_rows) { cudaFree(p->d_hist_rows); p->d_hist_rows = nullptr; }
     if (p->d_hist) { cudaFree(p->d_hist); p->d_hist = nullptr; }
     p->hist_n = p->hist_cap = p->hist_count = 0;
+    p->hook_epoch++;
     if (capacity <= 0) return 0;
     if (save_every <= 0) return fail("saa_plan_set_history: save_every must be positive");
     if (!dofs) n_dofs = p->n_dof;
@@ -630,6 +640,11 @@ extern "C" int saa_plan_set_history(saa_plan *p, const int64_t *dofs, int64_t n_
     if (upload(&p->d_hist_rows, rows)) return -1;
     CK(cudaMalloc((void **)&p->d_hist, (size_t)capacity * n_dofs * sizeof(double)));
     p->hist_n = n_dofs; p->hist_cap = capacity; p->hist_every = save_every;
+    p->hook_h.hist_every = save_every; p->hook_h.hist_cap = capacity;
+    p->hook_h.hist_first = (p->step_index + save_every - 1) / save_every;      // first recorded step is the next multiple of save_every
+    p->hook_epoch++;
+    CK(cudaMemcpyAsync(p->d_hook, &p->hook_h, sizeof(SaaHookDev), cudaMemcpyHostToDevice, plan_stream(p)));
+    CK(cudaStreamSynchronize(plan_stream(p)));
     return 0;
 }
 extern "C" int64_t saa_plan_history_count(const saa_plan *p) { return p ? p->hist_count : -1; }
@@ -681,24 +696,47 @@ extern "C" int saa_plan_set_prediction(saa_plan *p, const int64_t *dofs, int64_t
         return fail("saa_plan_set_prediction: n_dofs changed without a DOF list");
     }
     p->d_pred_table = table_dev; p->pred_rows = n_rows; p->pred_next = 0;
+    p->hook_h.pred_table = table_dev; p->hook_h.pred_rows = n_rows; p->hook_h.pred_base_step = p->step_index;
+    if (dofs) p->hook_epoch++;
+    CK(cudaMemcpyAsync(p->d_hook, &p->hook_h, sizeof(SaaHookDev), cudaMemcpyHostToDevice, plan_stream(p)));
+    CK(cudaStreamSynchronize(plan_stream(p)));      // hook_h is reused by the next call
     return 0;
 }
 
-// after a step: the new d0 is d_buf[cur]
+// after a step: the new d0 is d_buf[cur]; the step read its clock from slot cur ^ 1.  Only kernels are enqueued here
+// (graph-capturable); the host mirrors of the counters are advanced by count_step().
+static void enqueue_hooks(saa_plan *p, cudaStream_t st, int mode)
+{
+    const SaaClock *clk_old = p->d_clk + (p->cur ^ 1);
+    if (mode == SAA_MODE_PREDICT && p->pred_n > 0) {                         // Online_predictor.py:298
+        saa_k_hook_scatter<<<nblk(p->pred_n, 256), 256, 0, st>>>(p->pred_n, p->d_pred_rows, p->d_hook, clk_old, p->d_buf[p->cur]);
+        p->launches++;
+    }
+    if (p->hist_cap > 0 && p->hist_n > 0) {                                  // Data_prepare.py:238-240
+        saa_k_hook_gather<<<nblk(p->hist_n, 256), 256, 0, st>>>(p->hist_n, p->d_hist_rows, p->d_hook, clk_old, p->d_buf[p->cur], p->d_hist);
+        p->launches++;
+    }
+}
+static void count_step(saa_plan *p, int mode)
+{
+    if (mode == SAA_MODE_PREDICT) p->pred_next++;
+    if (p->hist_cap > 0 && (p->step_index % p->hist_every) == 0) p->hist_count++;
+    p->step_index++;
+}
+static int check_prediction(saa_plan *p, int mode, int64_t n_steps)
+{
+    if (mode != SAA_MODE_PREDICT) return 0;
+    if (!p->d_pred_table && p->pred_n > 0) return fail("SAA_MODE_PREDICT: no prediction table set");
+    if (p->hook_h.pred_base_step + p->pred_next != p->step_index) return fail("SAA_MODE_PREDICT: steps of another mode ran since the table was set; set it again");
+    if (p->pred_next + n_steps > p->pred_rows) return fail("SAA_MODE_PREDICT: prediction table exhausted (%lld rows left, %lld steps asked)",
+                                                            (long long)(p->pred_rows - p->pred_next), (long long)n_steps);
+    return 0;
+}
 static int after_step(saa_plan *p, cudaStream_t st, int mode)
 {
-    if (mode == SAA_MODE_PREDICT) {
-        if (!p->d_pred_table || p->pred_next >= p->pred_rows) return fail("SAA_MODE_PREDICT: prediction table exhausted or not set");
-        // Online_predictor.py:298 — d1[loc_dof_shared] = d_shared[row]
-        saa_k_scatter_rows<<<nblk(p->pred_n, 256), 256, 0, st>>>(p->pred_n, p->d_pred_rows, p->d_pred_table + p->pred_next * p->pred_n, p->d_buf[p->cur]);
-        p->launches++; p->pred_next++;
-    }
-    if (p->hist_cap > 0 && (p->step_index % p->hist_every) == 0) {      // Data_prepare.py:238-240
-        const int64_t slot = p->hist_count % p->hist_cap;
-        saa_k_gather_rows<<<nblk(p->hist_n, 256), 256, 0, st>>>(p->hist_n, p->d_hist_rows, p->d_buf[p->cur], p->d_hist + slot * p->hist_n);
-        p->launches++; p->hist_count++;
-    }
-    p->step_index++;
+    if (check_prediction(p, mode, 1)) return -1;
+    enqueue_hooks(p, st, mode);
+    count_step(p, mode);
     return 0;
 }
 
@@ -750,12 +788,64 @@ static void launch_local_step(saa_plan *p, cudaStream_t st)
 
 static bool needs_hooks(const saa_plan *p, int mode) { return mode == SAA_MODE_PREDICT || p->hist_cap > 0; }
 
+// one step of `mode` (local / predict / peer-synchronised) with its hooks: kernels only
+static void launch_peer_step(saa_plan *p, cudaStream_t st);
+static void enqueue_step_with_hooks(saa_plan *p, cudaStream_t st, int mode)
+{
+    if (mode == SAA_MODE_SYNC) launch_peer_step(p, st);
+    else launch_local_step(p, st);
+    enqueue_hooks(p, st, mode);
+}
+// steps with history / prediction hooks, replayed two at a time from a CUDA graph (the hooks take their row / slot
+// from the device clock, the table pointer from the device hook state: nothing in the graph changes between replays)
+static int step_hook_graph(saa_plan *p, int64_t n_steps, int mode)
+{
+    cudaStream_t st = p->stream;
+    int64_t done = 0;
+    saa_plan::StepGraph *g = nullptr;
+    const int c0 = p->cur;
+    for (auto &q : p->step_graphs)
+        if (q.mode == mode && q.cur == c0 && q.epoch == p->hook_epoch) g = &q;
+    if (!g) {
+        for (size_t i = 0; i < p->step_graphs.size();)                       // drop graphs of older hook configurations
+            if (p->step_graphs[i].epoch != p->hook_epoch) { cudaGraphExecDestroy(p->step_graphs[i].exec); p->step_graphs.erase(p->step_graphs.begin() + i); }
+            else ++i;
+        cudaGraph_t graph;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = p->launches;
+        enqueue_step_with_hooks(p, st, mode);
+        enqueue_step_with_hooks(p, st, mode);
+        const int per = (int)(p->launches - l0);
+        p->launches = l0;
+        CK(cudaStreamEndCapture(st, &graph));
+        saa_plan::StepGraph q{mode, c0, p->hook_epoch, nullptr, per};
+        CK(cudaGraphInstantiate(&q.exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        p->step_graphs.push_back(q);
+        g = &p->step_graphs.back();
+    }
+    for (; done + 2 <= n_steps; done += 2) {
+        CK(cudaGraphLaunch(g->exec, st));
+        p->launches += g->launches;
+        count_step(p, mode);
+        count_step(p, mode);
+    }
+    for (; done < n_steps; ++done) {
+        enqueue_step_with_hooks(p, st, mode);
+        count_step(p, mode);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
 {
     cudaStream_t st = p->stream;
     const bool hooks = needs_hooks(p, mode);
-    if (launch == SAA_LAUNCH_AUTO) launch = hooks ? SAA_LAUNCH_PER_STEP : (n_steps >= 8 ? SAA_LAUNCH_GRAPH : SAA_LAUNCH_PER_STEP);
-    if (hooks && launch != SAA_LAUNCH_PER_STEP) return fail("history / prediction hooks need SAA_LAUNCH_PER_STEP");
+    if (launch == SAA_LAUNCH_AUTO) launch = (n_steps >= 8 ? SAA_LAUNCH_GRAPH : SAA_LAUNCH_PER_STEP);
+    if (hooks && launch == SAA_LAUNCH_PERSISTENT) return fail("history / prediction hooks are not available in the persistent loop");
+    if (check_prediction(p, mode, n_steps)) return -1;
+    if (hooks && launch == SAA_LAUNCH_GRAPH && n_steps >= 2) return step_hook_graph(p, n_steps, mode);
     if (launch == SAA_LAUNCH_PERSISTENT) {
         if (p->coop_blocks <= 0) return fail("cooperative launch not available");
         double *a = p->d_buf[p->cur], *b = p->d_buf[p->cur ^ 1];
@@ -795,7 +885,8 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
     }
     for (; done < n_steps; ++done) {
         launch_local_step(p, st);
-        if (after_step(p, st, mode)) return -1;
+        enqueue_hooks(p, st, mode);
+        count_step(p, mode);
     }
     CK(cudaGetLastError());
     return 0;
@@ -874,6 +965,7 @@ static int step_sync_peer(saa_plan *p, int64_t n_steps, int launch)
     cudaStream_t st = p->stream;
     const bool hooks = p->hist_cap > 0;
     int64_t done = 0;
+    if (hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) return step_hook_graph(p, n_steps, SAA_MODE_SYNC);
     if (!hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) {
         const int c = p->cur;
         if (!p->graph_peer[c]) {

@@ -56,7 +56,18 @@ struct SaaDev {
 // CUDA graph; every step reads slot `cur` and writes slot `cur ^ 1`.
 struct SaaClock {
     double tn;
-    unsigned long long sync_step;
+    unsigned long long sync_step;   // synchronised steps so far (message / arrival-flag numbering of the peer transport)
+    unsigned long long step_idx;    // all steps so far = the loop index i of Data_prepare.py:223 / Online_predictor.py:251
+};
+
+// History / prediction hooks read their indices from device memory, so that steps with hooks are graph-replayable too.
+struct SaaHookDev {
+    const double *pred_table;       // (pred_rows, pred_n) predictions of the shared DOFs (Online_predictor.py:280)
+    long long pred_base_step;       // step index whose d1 takes row 0
+    long long pred_rows;
+    long long hist_every;           // record when step_idx % hist_every == 0 (Data_prepare.py:238)
+    long long hist_first;           // step_idx / hist_every of snapshot 0
+    long long hist_cap;             // ring capacity in snapshots
 };
 
 // halo description on the device
@@ -418,6 +429,7 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
     if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         clk_out->tn = __dadd_rn(tn, P.dt);
         clk_out->sync_step = step + count_sync;
+        clk_out->step_idx = clk_in->step_idx + 1ull;
     }
     if (blockIdx.x < n_main) {
         const int lane = threadIdx.x & 31;
@@ -497,6 +509,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) saa_k_step_stream(SaaDev P, con
     if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         clk_out->tn = __dadd_rn(tn, P.dt);
         clk_out->sync_step = clk_in->sync_step + count_sync;
+        clk_out->step_idx = clk_in->step_idx + 1ull;
     }
     const double ramp = saa_ramp(tn);
     // ---- this warp's contiguous range of slices: equal shares of the block-rows (a block-row = 32 block-lanes)
@@ -614,7 +627,10 @@ __global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, 
         double *t = d0; d0 = dn; dn = t;
         grid.sync();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) clk_io->tn = tn;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        clk_io->tn = tn;
+        clk_io->step_idx += (unsigned long long)n_steps;
+    }
 }
 
 // ---- small data-movement kernels -----------------------------------------------------------------------
@@ -631,6 +647,26 @@ __global__ void saa_k_gather_to_external(int64_t n_ext, const int32_t *__restric
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_ext) dst_ext[i] = src_int[iperm[i]];
 }
+// Hooks after a step whose input clock was *clk_old (its step_idx is the loop index i of this step):
+//   Online_predictor.py:298   d1[loc_dof_shared] = d_shared[i - first predicted step]
+__global__ void saa_k_hook_scatter(int64_t n, const int32_t *__restrict__ rows, const SaaHookDev *__restrict__ hk,
+                                   const SaaClock *__restrict__ clk_old, double *__restrict__ d1)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = (long long)clk_old->step_idx - hk->pred_base_step;
+    if (i < n && r >= 0 && r < hk->pred_rows) d1[rows[i]] = hk->pred_table[r * n + i];
+}
+//   Data_prepare.py:238-240 / Online_predictor.py:260,301   d1_save[:, i / save_every] = d1  (device ring)
+__global__ void saa_k_hook_gather(int64_t n, const int32_t *__restrict__ rows, const SaaHookDev *__restrict__ hk,
+                                  const SaaClock *__restrict__ clk_old, const double *__restrict__ d1, double *__restrict__ hist)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = (long long)clk_old->step_idx;
+    if (i >= n || (s % hk->hist_every) != 0) return;
+    const long long slot = (s / hk->hist_every - hk->hist_first) % hk->hist_cap;
+    hist[slot * n + i] = d1[rows[i]];
+}
+
 // history snapshot / prediction overwrite: rows[] are internal ids
 __global__ void saa_k_gather_rows(int64_t n, const int32_t *__restrict__ rows, const double *__restrict__ src, double *__restrict__ dst)
 {

@@ -97,7 +97,9 @@ class SyncAvoidingRun:
                 self.tables.append([t.cpu().numpy() for t in tables])
             self._live = tables
             for pl, d, t in zip(self.plans, self.dofs, tables):
-                pl.set_prediction(d, t.data_ptr(), t.shape[0])
+                # the DOF list is handed over once; afterwards only the table changes (keeps the plan's step graphs valid)
+                pl.set_prediction(None if getattr(pl, "_sa_dofs_set", False) else d, t.data_ptr(), t.shape[0])
+                pl._sa_dofs_set = True
             n_blk = min(self.block, test_num - self.i)
             done = 0
             while done < n_blk:                                                # :284-316
