@@ -322,3 +322,29 @@ def test_node_order_hint_changes_layout_not_results(name, order):
         n = r["F"].size
         K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
         splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], 0.5, node_order=np.zeros(n // 3, dtype=np.int32))
+
+
+def test_hook_steps_from_graph_equal_per_step_launches():
+    """Prediction overwrite + history recording: replayed from a CUDA graph (indices read from the device clock) vs one
+    launch per step — same bits, same ring contents, same counters."""
+    import torch
+    g = load_golden("beam_coarse_P2")
+    r = g["ranks"][0]
+    dofs = r["loc_dof_shared"]
+    rng = np.random.default_rng(5)
+    table = torch.from_numpy(rng.standard_normal((41, dofs.size)) * 1e-4).cuda()
+    outs = []
+    for launch in (splan.LAUNCH_GRAPH, splan.LAUNCH_PER_STEP):
+        pl = golden_plans_single(g, 0)
+        pl.step(7, splan.MODE_LOCAL)                              # hooks configured mid-run, at an odd step
+        pl.set_history(dofs, capacity=16, save_every=2)
+        pl.set_prediction(dofs, table.data_ptr(), 41)
+        pl.step(41, splan.MODE_PREDICT, launch)
+        pl.synchronize()
+        assert pl.history_count == 21                             # steps 8, 10, ..., 48
+        outs.append((pl.d0(), pl.read_history(21 - 16, 16)))
+        with pytest.raises(splan.SaaError, match="exhausted"):
+            pl.step(2, splan.MODE_PREDICT, launch)
+    assert bits_equal(outs[0][0], outs[1][0]) and bits_equal(outs[0][1], outs[1][1])
+    # recorded values of predicted steps are the table rows themselves: step 46 = row 46 - 7 = 39
+    assert bits_equal(outs[0][1][-1], table[39].cpu().numpy())
