@@ -1,0 +1,106 @@
+"""CPU checks of the host-side plumbing around the device path: slab generator and numbering of the device set-up
+(torch ops, run here on CPU tensors), layer balancing, Morton order, the serial communicator, the driver launcher."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import saa_b200  # noqa: F401
+from saa_b200 import comm, device_setup as ds, maps, mesh
+from util import ROOT
+
+PKG = os.path.join(ROOT, "synchronization-avoiding-algorithms_b200")
+
+
+@pytest.mark.parametrize("m,size", [(2, 1), (2, 3), (3, 4)])
+def test_slab_generator_and_numbering_equal_host_maps(m, size):
+    import torch
+    pts, cells, fac = mesh.structured_beam(m)
+    ep = ds.layer_slab_partition(m, size)
+    assert ep.min() == 0 and ep.max() == size - 1 and np.all(np.diff(ep) >= 0)
+    for r in range(size):
+        c = ds.structured_slab_cells(m, r, size, device="cpu")
+        assert np.array_equal(c.numpy(), cells[ep == r])                         # ascending global element order
+        nodes, cl = ds.local_numbering(c)
+        ele, ref_nodes = maps.rankwise_dist(r, ep, cells)
+        assert np.array_equal(nodes.numpy(), ref_nodes)                           # first-appearance order, exact
+        assert cl.dtype == torch.int32 and np.array_equal(nodes.numpy()[cl.numpy()], cells[ep == r])
+        P = ds.structured_points(m, nodes)
+        assert np.array_equal(P.numpy(), pts[ref_nodes])
+        assert ds.min_edge_meshsize(cl, P, chunk=50) == mesh.meshsize(cells[ep == r], pts)
+
+
+def test_layer_bounds_follow_weights():
+    try:
+        assert ds.layer_bounds(65, 8) == [(r * 1625) // 8 for r in range(9)]
+        ds.set_layer_weights([1, 1, 0.5, 1])
+        b = ds.layer_bounds(4, 4)
+        w = np.diff(b)
+        assert b[0] == 0 and b[-1] == 100 and w[2] < w[0] and abs(w[2] - 100 * 0.5 / 3.5) <= 1 and w.min() >= 1
+        ds.set_layer_weights([1e-9, 1, 1])
+        assert np.diff(ds.layer_bounds(1, 3)).min() >= 1                          # nobody ends up without a layer
+    finally:
+        ds.set_layer_weights(None)
+
+
+def test_morton_order_is_a_local_permutation():
+    import torch
+    rng = np.random.default_rng(0)
+    pts = torch.from_numpy(rng.random((4096, 3)))
+    o = ds.morton_node_order(pts)
+    assert sorted(o.tolist()) == list(range(4096))
+    p = pts.numpy()
+    jump_sorted = np.linalg.norm(np.diff(p[o], axis=0), axis=1).mean()
+    jump_given = np.linalg.norm(np.diff(p, axis=0), axis=1).mean()
+    assert jump_sorted < 0.3 * jump_given
+    # a structured grid in lexicographic order: the Z-curve visits every node once
+    g = torch.from_numpy(np.stack(np.meshgrid(np.arange(4.), np.arange(4.), np.arange(4.), indexing="ij"), -1).reshape(-1, 3))
+    assert sorted(ds.morton_node_order(g).tolist()) == list(range(64))
+
+
+def test_serial_communicator_has_the_mpi4py_surface_the_drivers_use():
+    c = comm.SerialComm()
+    assert (c.Get_rank(), c.Get_size()) == (0, 1)
+    assert c.bcast({"a": 1}, root=0) == {"a": 1} and c.gather(5, root=0) == [5] and c.allgather("x") == ["x"]
+    buf = np.empty(3)
+    c.Gatherv(np.arange(3.0), buf, root=0)
+    assert np.array_equal(buf, np.arange(3.0))
+    c.Gather(np.float64(2.5), buf[:1], root=0)
+    assert buf[0] == 2.5
+    c.Barrier()
+    assert c.exchange(np.zeros(0), np.zeros(0, dtype=np.int32), np.zeros(1, dtype=np.int64)).size == 0
+
+
+def test_run_driver_puts_the_package_first_and_compat_last(tmp_path):
+    """A script living next to a decoy `Tools` directory must still get the drop-in `Tools`."""
+    os.makedirs(tmp_path / "Tools")
+    (tmp_path / "Tools" / "__init__.py").write_text("DECOY = True\n")
+    (tmp_path / "Tools" / "commons.py").write_text("raise RuntimeError('decoy Tools imported')\n")
+    (tmp_path / "drv.py").write_text(
+        "from Tools.commons import *\nimport Tools, sys, h5py, meshio\n"
+        "assert not hasattr(Tools, 'DECOY')\nassert linear_ramp(0.25) == 0.25 and linear_ramp(3) == 1.0\n"
+        "assert sys.argv[1:] == ['--flag', '7']\nprint('driver ok', node_to_dof(3, [0, 1, 2], [2]).tolist())\n")
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run([sys.executable, os.path.join(PKG, "run_driver.py"), str(tmp_path / "drv.py"), "--flag", "7"], cwd=str(tmp_path),
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "driver ok [6, 7, 8]" in r.stdout
+
+
+def test_rcm_order_is_a_permutation_that_reduces_bandwidth():
+    from saa_b200 import assembly, plan, problem
+    pts, cells, _ = mesh.structured_beam(2)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(len(pts))                                             # scramble the numbering
+    K = assembly.local_stiffness_csr(perm, cells, pts, *problem.lame(1e6, 0.3))
+    o = plan.rcm_node_order(K)
+    assert sorted(o.tolist()) == list(range(len(pts)))
+    G = (K != 0).tocoo()
+    pos = np.empty(len(pts), dtype=np.int64)
+    pos[o] = np.arange(len(pts))
+    bw_rcm = np.abs(pos[G.row // 3] - pos[G.col // 3]).max()
+    bw_raw = np.abs(G.row // 3 - G.col // 3).max()
+    assert bw_rcm < 0.5 * bw_raw
