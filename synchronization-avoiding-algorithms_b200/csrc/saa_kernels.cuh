@@ -666,15 +666,3 @@ __global__ void saa_k_hook_gather(int64_t n, const int32_t *__restrict__ rows, c
     const long long slot = (s / hk->hist_every - hk->hist_first) % hk->hist_cap;
     hist[slot * n + i] = d1[rows[i]];
 }
-
-// history snapshot / prediction overwrite: rows[] are internal ids
-__global__ void saa_k_gather_rows(int64_t n, const int32_t *__restrict__ rows, const double *__restrict__ src, double *__restrict__ dst)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[rows[i]];
-}
-__global__ void saa_k_scatter_rows(int64_t n, const int32_t *__restrict__ rows, const double *__restrict__ src, double *__restrict__ dst)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[rows[i]] = src[i];
-}
