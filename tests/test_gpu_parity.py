@@ -341,8 +341,8 @@ def test_hook_steps_from_graph_equal_per_step_launches():
         pl.set_prediction(dofs, table.data_ptr(), 41)
         pl.step(41, splan.MODE_PREDICT, launch)
         pl.synchronize()
-        assert pl.history_count == 21                             # steps 8, 10, ..., 48
-        outs.append((pl.d0(), pl.read_history(21 - 16, 16)))
+        assert pl.history_count == 20                             # loop indices 7..47 ran: 8, 10, ..., 46 are recorded
+        outs.append((pl.d0(), pl.read_history(20 - 16, 16)))
         with pytest.raises(splan.SaaError, match="exhausted"):
             pl.step(2, splan.MODE_PREDICT, launch)
     assert bits_equal(outs[0][0], outs[1][0]) and bits_equal(outs[0][1], outs[1][1])
