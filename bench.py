@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed host-call steps (0: 200 for m <= 32, else 30)")
     ap.add_argument("--launch", default="auto", choices=["auto", "per_step", "graph", "persistent"])
     ap.add_argument("--setup", default="device", choices=["device", "host"], help="where the problem is assembled")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="CPU time budget of the oracle runs (0: 15 s native arm, 20 s reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="N = 1: skip the extra 21 M-DOF measurement")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo transport for N > 1")
@@ -202,7 +202,7 @@ def run_reference(args, emit):
     if csr is None:
         _, info = setup_host(m, 1, 0, 0, make_plan=False)
         csr, n_nodes, n_el, dt = info["csr"], info["n_nodes"], info["n_elem"], info["dt"]
-    cb, k, secs = cpu_baseline(csr, n_nodes, dt, max(args.cpu_seconds, 20.0))
+    cb, k, secs = cpu_baseline(csr, n_nodes, dt, args.cpu_seconds or 20.0)
     n_dof = 3 * n_nodes
     line = {"impl": "reference", "metric": "DOF-steps/sec", "value": cb["value"], "unit": "DOF-steps/s",
             "n_gpus": args.gpus, "steps": k, "warmup": 3, "ms_per_step": 1e3 * secs / k, "higher_is_better": True,
@@ -451,7 +451,7 @@ def main():
                 csr, nn, dt24 = i24["csr"], i24["n_nodes"], i24["dt"]
             else:
                 nn, dt24 = info["n_nodes"], dtv
-            cb, _, _ = cpu_baseline(csr, nn, dt24, args.cpu_seconds)
+            cb, _, _ = cpu_baseline(csr, nn, dt24, args.cpu_seconds or 15.0)
             line["cpu_baseline"] = cb
         emit(line)
     if world > 1:

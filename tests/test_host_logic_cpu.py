@@ -104,3 +104,23 @@ def test_rcm_order_is_a_permutation_that_reduces_bandwidth():
     bw_rcm = np.abs(pos[G.row // 3] - pos[G.col // 3]).max()
     bw_raw = np.abs(G.row // 3 - G.col // 3).max()
     assert bw_rcm < 0.5 * bw_raw
+
+
+def test_bench_reference_arm_prints_one_json_line_without_a_gpu():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) needs no GPU and prints exactly one
+    JSON line with the contract's keys."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--refine", "3", "--cpu-seconds", "0.3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "DOF-steps/sec" and d["unit"] == "DOF-steps/s" and d["higher_is_better"]
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+    # ranks other than 0 of a torchrun launch do nothing and exit 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ""
