@@ -12,10 +12,34 @@ from __future__ import annotations
 from . import plan as _plan
 
 
+def peer_access_everywhere(pl):
+    """True when every rank can map the receive areas of all its neighbours (same node, P2P-capable GPUs).
+    Collective; all ranks get the same answer."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    me = dict(rank=pl.rank, host=socket.gethostname(), dev=pl.device, nb=[int(r) for r in pl.halo_layout()[0]])
+    infos = [None] * dist.get_world_size()
+    dist.all_gather_object(infos, me)
+    by_rank = {i["rank"]: i for i in infos}
+    ok = True
+    for r in me["nb"]:
+        o = by_rank[r]
+        if o["host"] != me["host"]:
+            ok = False
+        elif o["dev"] != me["dev"] and not torch.cuda.can_device_access_peer(me["dev"], o["dev"]):
+            ok = False
+    flags = [None] * dist.get_world_size()
+    dist.all_gather_object(flags, ok)
+    return all(flags)
+
+
 def attach_transport(pl, transport="peer"):
     import torch.distributed as dist
     if pl.size == 1:
         return "none"
+    if transport == "peer" and not peer_access_everywhere(pl):
+        transport = "nccl"                      # several nodes, or GPUs without peer access: NCCL carries the messages
     if transport == "peer":
         exports = [None] * dist.get_world_size()
         dist.all_gather_object(exports, pl.peer_export())
