@@ -43,6 +43,10 @@ CASES = {
     "struct_m2_P4": ("struct2", 4, "slab", [1, 100, 1000], []),
     "struct_m3_P1": ("struct3", 1, "metis", [1, 100, 500], []),
     "struct_m3_P3": ("struct3", 3, "metis", [1, 100, 500], []),
+    # the larger oracle case of SURVEY.md section 8c (2525 nodes, 7575 DOF; the reference's dense set-up takes ~2 minutes)
+    "struct_m4_P2": ("struct4", 2, "slab", [1, 100, 1000, 3000], [50]),
+    # 6517 nodes, 19 551 DOF, 32 400 tets — near the practical ceiling of the reference's dense (3N)^2 set-up
+    "struct_m6_P3": ("struct6", 3, "metis", [1, 100, 1000], []),
 }
 
 
