@@ -229,3 +229,85 @@ def test_reference_shared_extraction_script_runs_unchanged_on_this_package(tmp_p
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = np.load(str(tmp_path / "Results" / "sol_on_shared" / "rank=0-shared_dof.hdf5.npz"))["Displacement"]
     assert np.array_equal(out, D[r0["loc_dof_shared"], :])
+
+
+def _online_golden():
+    import torch
+    from Tools.DNN_tools import LSTM_encoder_decoder
+    z = np.load(os.path.join(GOLDEN, "online_beam_coarse_P2.npz"))
+    g = load_golden("beam_coarse_P2")
+    models = []
+    for q in range(2):
+        m = LSTM_encoder_decoder(g["ranks"][q]["loc_dof_shared"].size, int(z["hidden"]), 2, True, 0.0, 0.0)
+        m.load_state_dict({k[len(f"sd{q}__"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"sd{q}__")})
+        models.append(m)
+    return z, g, models
+
+
+def test_sync_avoiding_trajectory_of_the_reference_cpu_emulation():
+    """Golden trajectory recorded from the reference's own Online_predictor loop (oracle/gen_golden_online.py).  Here the
+    FE steps come from the oracle and the refill tables from this package's batched predictor on the CPU: the
+    synchronised warm-up is bit-identical, the predicted phase agrees to float32 rounding of the surrogate."""
+    from Tools.DNN_prediction import predict_block
+    import torch
+    z, g, models = _online_golden()
+    n_p, n_f, n_s, T = int(z["n_p"]), int(z["n_f"]), int(z["n_s"]), int(z["test_num"])
+    smax, smin = float(z["scale_max"]), float(z["scale_min"])
+    dofs = [r["loc_dof_shared"] for r in g["ranks"]]
+    o = oracle_module().OracleProblem(len(g["points"]), g["ranks"], g["dt"], float(g["alpha"]))
+    hist = [np.zeros((T, d.size)) for d in dofs]
+    i = 0
+    while i < n_p * n_s:
+        o.run(1)
+        for q in range(2):
+            hist[q][i] = o.d0(q)[dofs[q]]
+        i += 1
+    for q in range(2):
+        assert bits_equal(hist[q][:i], z[f"d_sol_r{q}"][:i])                     # synchronised phase: exact
+    while i < T:
+        tabs = [predict_block(models[q], torch.from_numpy(hist[q][i - n_p * n_s:i].copy()), n_p, n_f, n_s, smax, smin).numpy() for q in range(2)]
+        for k in range(min(n_f * n_s, T - i)):
+            o.run(1, model=True)
+            for q in range(2):
+                d0, dn, tn = o.state(q)
+                d0[dofs[q]] = tabs[q][k]
+                o.set_state(q, d0, dn, tn)
+                hist[q][i] = tabs[q][k]
+            i += 1
+    span = smax - smin
+    for q in range(2):
+        assert np.abs(hist[q] - z[f"d_sol_r{q}"]).max() <= 2e-5 * span
+        ref = z[f"final_r{q}"]
+        assert np.linalg.norm(o.d0(q) - ref) <= 1e-4 * np.linalg.norm(ref)
+
+
+@pytest.mark.gpu
+def test_sync_avoiding_trajectory_of_the_reference_on_gpu():
+    """The same golden trajectory against the device loop (SyncAvoidingRun, both partitions on one GPU)."""
+    import scipy.sparse as sp
+    import saa_b200  # noqa: F401
+    from saa_b200 import maps, plan as splan, sync_avoiding
+    z, g, models = _online_golden()
+    n_p, n_f, n_s, T = int(z["n_p"]), int(z["n_f"]), int(z["n_s"]), int(z["test_num"])
+    smax, smin = float(z["scale_max"]), float(z["scale_min"])
+    lists = [r["nodes"] for r in g["ranks"]]
+    plans = []
+    for q, r in enumerate(g["ranks"]):
+        n = r["F"].size
+        K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+        plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), halo=maps.halo_plan(q, 2, lists), rank=q, size=2))
+    grp = splan.PlanGroup(plans)
+    run = sync_avoiding.SyncAvoidingRun(plans, grp, [r["loc_dof_shared"] for r in g["ranks"]], models, [(smax, smin)] * 2, n_p, n_f, n_s)
+    run.run(n_p * n_s)
+    grp.synchronize()
+    for q in range(2):                                                           # synchronised phase: exact
+        assert bits_equal(plans[q].read_history(0, n_p * n_s), z[f"d_sol_r{q}"][:n_p * n_s])
+    run.run(T)
+    grp.synchronize()
+    span = smax - smin
+    cap = n_p * n_s + n_f * n_s
+    for q in range(2):
+        H = plans[q].read_history(T - cap, cap)
+        assert np.abs(H - z[f"d_sol_r{q}"][T - cap:]).max() <= 5e-5 * span
+        ref = z[f"final_r{q}"]
+        assert np.linalg.norm(plans[q].d0() - ref) <= 2e-4 * np.linalg.norm(ref)
