@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY; run in the authoring container:  python oracle/gen_gol
 The loop of Online_predictor.py:251-318 is restated by CALLING the reference's own functions
 (parallel_explicit_solver_dis_pre with MODEL=False / True, syn_cpus through the in-process communicator of
 ref_harness, encoder_decoder_predictor, LSTM_encoder_decoder) for beam_coarse with the fixture's 2-way partition;
-the surrogates have seeded random weights (the reference ships no trained model).  -> tests/golden/online_beam_coarse_P2.npz
+the surrogates have seeded random weights (the reference ships no trained model).  -> tests/golden/online_beam_coarse_np2.npz
 """
 import os
 import sys
@@ -81,5 +81,5 @@ for q in range(P):
     out[f"d_sol_r{q}"] = d_sol[q]
     for k, v in models[q].state_dict().items():
         out[f"sd{q}__" + k] = v.numpy()
-np.savez_compressed(os.path.join(GOLDEN, "online_beam_coarse_P2.npz"), **out)
-print("online golden:", test_num, "steps,", [float(np.abs(d_0[q]).max()) for q in range(P)], os.path.getsize(os.path.join(GOLDEN, "online_beam_coarse_P2.npz")) // 1024, "KiB")
+np.savez_compressed(os.path.join(GOLDEN, "online_beam_coarse_np2.npz"), **out)
+print("online golden:", test_num, "steps,", [float(np.abs(d_0[q]).max()) for q in range(P)], os.path.getsize(os.path.join(GOLDEN, "online_beam_coarse_np2.npz")) // 1024, "KiB")

@@ -234,7 +234,7 @@ def test_reference_shared_extraction_script_runs_unchanged_on_this_package(tmp_p
 def _online_golden():
     import torch
     from Tools.DNN_tools import LSTM_encoder_decoder
-    z = np.load(os.path.join(GOLDEN, "online_beam_coarse_P2.npz"))
+    z = np.load(os.path.join(GOLDEN, "online_beam_coarse_np2.npz"))
     g = load_golden("beam_coarse_P2")
     models = []
     for q in range(2):
