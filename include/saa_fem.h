@@ -157,6 +157,15 @@ int saa_plan_get_state_dev(saa_plan *plan, double *d0_dev, double *dn_dev, doubl
  */
 int saa_plan_step(saa_plan *plan, int64_t n_steps, int mode, int launch);
 int saa_plan_synchronize(saa_plan *plan);
+/*
+ * Execution options of synchronised steps (same arithmetic, same bits; used for cross-path checks and measurements):
+ *   SAA_OPT_PEER_FUSED   1 (default): one fused launch per step with the peer transport; 0: boundary / interior /
+ *                        shared-row kernels as three launches.
+ *   SAA_OPT_PREFER_NCCL  1: use the NCCL transport (saa_plan_init_nccl) although peer memory is attached too.
+ */
+#define SAA_OPT_PEER_FUSED 1
+#define SAA_OPT_PREFER_NCCL 2
+int saa_plan_set_option(saa_plan *plan, int option, int value);
 /* the cudaStream_t the plan enqueues on (as void*), so that callers can record events on it */
 void *saa_plan_stream(saa_plan *plan);
 
@@ -167,6 +176,16 @@ void *saa_plan_stream(saa_plan *plan);
  */
 int saa_step_host(saa_plan *plan, const double *d0_host, const double *dn_host, double tn, int mode,
                   double *d1_host);
+/*
+ * Same call with a hint about the caller's rotation (Data_prepare.py:233-234, Online_predictor.py:265-266:
+ * `d_n = d_0; d_0 = d1`).  SAA_HOST_DN_IS_PREVIOUS_D0 asserts that dn_host holds, unchanged, the values passed as
+ * d0_host to the previous saa_step_host[_ex] call on this plan; the device still has them, so only d0 crosses PCIe.
+ * The hint is ignored (full upload) when anything else touched the plan's state since that call.  dn_host must
+ * still be a valid pointer.  Returns 1 when the dn upload was skipped, 0 when everything was uploaded, < 0 on error.
+ */
+#define SAA_HOST_DN_IS_PREVIOUS_D0 1
+int saa_step_host_ex(saa_plan *plan, const double *d0_host, const double *dn_host, double tn, int mode,
+                     double *d1_host, int flags);
 
 /*
  * Record rows of the solution on the device every `save_every` steps (the d1_save / d_sol_shared

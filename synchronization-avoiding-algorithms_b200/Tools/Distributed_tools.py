@@ -44,18 +44,23 @@ _halo_only_plans = {}
 
 
 def _halo_plan_for(size, rank, Local_nodes):
-    """Device plan that only carries the interface description of this rank (no matrix)."""
+    """Device plan that only carries the interface description of this rank (no matrix).  Cached under a digest of
+    the whole node list; whether to (re)build is decided COLLECTIVELY, so that the allgather below is entered by
+    every rank or by none (a rank-local cache miss would deadlock the others)."""
+    import hashlib
     from scipy.sparse import csr_matrix
     from saa_b200 import plan as _plan
-    nodes = np.asarray(Local_nodes, dtype=np.int64)
-    key = (size, rank, nodes.size, int(nodes[:64].sum()), int(nodes[-64:].sum()))
+    nodes = np.ascontiguousarray(Local_nodes, dtype=np.int64)
+    key = (size, rank, nodes.size, hashlib.blake2b(nodes.tobytes(), digest_size=16).digest())
     p = _halo_only_plans.get(key)
-    if p is None:
-        lists = comm.allgather(nodes) if hasattr(comm, "allgather") else comm.bcast(comm.gather(nodes, root=0), root=0)
-        n = 3 * nodes.size
-        p = _plan.StepPlan(csr_matrix((n, n)), np.zeros(n), np.ones(n), np.zeros(0, dtype=np.int64), 1.0, 0.0,
-                           halo=_maps.halo_plan(rank, size, lists), rank=rank, size=size)
-        _halo_only_plans[key] = p
+    gather = (lambda v: comm.allgather(v)) if hasattr(comm, "allgather") else (lambda v: comm.bcast(comm.gather(v, root=0), root=0))
+    if any(gather(p is None)):
+        lists = gather(nodes)
+        if p is None:
+            n = 3 * nodes.size
+            p = _plan.StepPlan(csr_matrix((n, n)), np.zeros(n), np.ones(n), np.zeros(0, dtype=np.int64), 1.0, 0.0,
+                               halo=_maps.halo_plan(rank, size, lists), rank=rank, size=size)
+            _halo_only_plans[key] = p
     return p
 
 

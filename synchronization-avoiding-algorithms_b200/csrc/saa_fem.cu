@@ -125,10 +125,11 @@ struct saa_plan {
     // halo device
     double *d_xbuf = nullptr, *d_send = nullptr;
     double *d_recv = nullptr;               // peer region: [2 parities x total_msg doubles | n_nb arrival flags (u64)]
-    unsigned int *d_done = nullptr;          // [0] boundary completion counter, [1] error word
+    unsigned int *d_done = nullptr;          // [0] boundary completion counter, [1] error word, [32] finished-block tickets
     unsigned long long *d_own_ready = nullptr;
     int kvariant = SAA_DEFAULT_KVARIANT;    // SAA_KVARIANT: schedule variant of the step kernel
-    bool peer_fused = true;                 // one fused launch per synchronised step (SAA_PEER_FUSED=0: three kernels)
+    bool peer_fused = true;                 // one fused launch per synchronised step (SAA_PEER_FUSED=0 / SAA_OPT_PEER_FUSED: three kernels)
+    bool prefer_nccl = false;               // SAA_OPT_PREFER_NCCL: synchronised steps use the NCCL transport although peer memory is attached
     int32_t *d_dst_nb = nullptr;
     // peer-memory transport
     bool peer = false;
@@ -166,6 +167,7 @@ struct saa_plan {
     saa_group *group = nullptr;
     cudaEvent_t ev_msg = nullptr;
     bool in_split_step = false;             // between saa_plan_step_begin_host and saa_plan_step_end_host
+    int64_t state_epoch = 1, host_epoch = 0; // saa_step_host_ex: the device still holds the previous call's d0 iff equal
     double *d_force = nullptr;              // [2 * n_rows] scratch of the stand-alone force synchronisation
 };
 
@@ -280,6 +282,7 @@ static void sigma_sort(std::vector<int64_t> &nodes, const std::vector<int32_t> &
 }
 
 static int finalize_tail(saa_plan *p, int64_t sh_pad);
+static int prepare_graphs(saa_plan *p, bool peer);
 static int finalize_device(saa_plan *p);
 
 extern "C" int saa_plan_finalize(saa_plan *p)
@@ -476,8 +479,8 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
         const size_t region = (size_t)(2 * p->total_msg) * sizeof(double) + (size_t)std::max(n_nb, 1) * sizeof(unsigned long long);
         CK(cudaMalloc((void **)&p->d_recv, region));
         CK(cudaMemset(p->d_recv, 0, region));
-        CK(cudaMalloc((void **)&p->d_done, 2 * sizeof(unsigned int)));
-        CK(cudaMemset(p->d_done, 0, 2 * sizeof(unsigned int)));
+        CK(cudaMalloc((void **)&p->d_done, 64 * sizeof(unsigned int)));
+        CK(cudaMemset(p->d_done, 0, 64 * sizeof(unsigned int)));
         CK(cudaMalloc((void **)&p->d_own_ready, sizeof(unsigned long long)));
         CK(cudaMemset(p->d_own_ready, 0, sizeof(unsigned long long)));
         if (upload(&p->d_dst_nb, dst_nb)) return -1;
@@ -486,7 +489,7 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
         p->H.recv = p->d_recv; p->H.recv_stride = p->total_msg;
         p->H.dst_ptr = p->d_dst_ptr; p->H.dst_pos = p->d_dst_pos; p->H.dst_nb = p->d_dst_nb;
         p->H.src_ptr = p->d_src_ptr; p->H.src_pos = p->d_src_pos;
-        p->H.n_nb = n_nb; p->H.done_ctr = p->d_done; p->H.err = p->d_done + 1; p->H.own_ready = p->d_own_ready;
+        p->H.n_nb = n_nb; p->H.done_ctr = p->d_done; p->H.err = p->d_done + 1; p->H.tail_ticket = p->d_done + 32; p->H.own_ready = p->d_own_ready;
         p->H.flags = (const unsigned long long *)(p->d_recv + 2 * p->total_msg);
     }
 
@@ -506,7 +509,7 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     // above it the column-prefetching one with 4 blocks per SM
     if (p->kvariant < 0) p->kvariant = (p->n_dof < 4000000) ? 2 : 4;
     p->finalized = true;
-    return 0;
+    return prepare_graphs(p, false);
 }
 
 extern "C" int saa_plan_destroy(saa_plan *p)
@@ -552,12 +555,16 @@ static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1
     if (!(p)) return fail(name ": null plan");                \
     if (!(p)->finalized) return fail(name ": plan not finalized")
 
-static int set_state_from_stage(saa_plan *p, cudaStream_t st, double tn)
+static int set_state_from_stage(saa_plan *p, cudaStream_t st, double tn, bool with_dn = true)
 {
     // d_stage holds [d0_ext | dn_ext]; padding rows of the internal buffers stay 0
+    p->state_epoch++;
     saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage, p->d_buf[p->cur]);
-    saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage + p->n_dof, p->d_buf[p->cur ^ 1]);
-    p->launches += 2;
+    p->launches++;
+    if (with_dn) {
+        saa_k_scatter_to_internal<<<nblk(p->n_dof, 256), 256, 0, st>>>(p->n_dof, p->d_iperm, p->d_stage + p->n_dof, p->d_buf[p->cur ^ 1]);
+        p->launches++;
+    }
     CK(cudaMemcpyAsync(&p->d_clk[p->cur].tn, &tn, sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaGetLastError());
     return 0;
@@ -745,15 +752,15 @@ static int after_step(saa_plan *p, cudaStream_t st, int mode)
 // Which one is fastest depends on the schedule ptxas happens to pick; profiles/r1/kernel_variants.md has the
 // measurements behind the default.
 static void launch_step_kernel(int variant, unsigned grid, cudaStream_t st, const SaaDev &D, const SaaHaloDev &H, const double *d0,
-                               double *dn, const SaaClock *ci, SaaClock *co, int64_t slice_begin, unsigned n_main, unsigned count_sync)
+                               double *dn, const SaaClock *ci, SaaClock *co, int64_t slice_begin, unsigned tail_workers, unsigned count_sync)
 {
     switch (variant) {
-    case 0: saa_k_step<0, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
-    case 1: saa_k_step<0, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
-    case 2: saa_k_step<0, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
-    case 3: saa_k_step<1, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
-    case 5: saa_k_step<1, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
-    default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, n_main, count_sync); break;
+    case 0: saa_k_step<0, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
+    case 1: saa_k_step<0, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
+    case 2: saa_k_step<0, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
+    case 3: saa_k_step<1, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
+    case 5: saa_k_step<1, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
+    default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
     }
 }
 template <int STAGES, int WARPS, int BR>
@@ -776,7 +783,7 @@ static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, u
     }
     const unsigned n_main = std::max(1u, nblk(p->n_slices - slice_begin, SAA_WARPS_PER_BLOCK));
     launch_step_kernel(p->kvariant, n_main, st, D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
-                       advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, n_main, count_sync);
+                       advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, 0u, count_sync);
     p->launches++;
 }
 
@@ -838,11 +845,45 @@ static int step_hook_graph(saa_plan *p, int64_t n_steps, int mode)
     return 0;
 }
 
+// Two consecutive steps (LOCAL, or peer-synchronised) starting at the current buffer parity as an instantiated,
+// uploaded CUDA graph.  Capture enqueues nothing, so this is also done ahead of time for BOTH parities
+// (prepare_graphs, at finalize / peer attach): the first saa_plan_step call then costs what every later one does.
+static void launch_peer_step(saa_plan *p, cudaStream_t st);
+static int capture_two_steps(saa_plan *p, bool peer)
+{
+    cudaStream_t st = p->stream;
+    cudaGraphExec_t *slot = peer ? &p->graph_peer[p->cur] : &p->graph_exec[p->cur];
+    if (*slot) return 0;
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int64_t l0 = p->launches;
+    for (int i = 0; i < 2; ++i) {
+        if (peer) launch_peer_step(p, st);
+        else launch_local_step(p, st);
+    }
+    p->launches = l0;
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(slot, g, 0));
+    CK(cudaGraphDestroy(g));
+    CK(cudaGraphUpload(*slot, st));
+    return 0;
+}
+static int prepare_graphs(saa_plan *p, bool peer)
+{
+    if (p->kvariant >= 6) return 0;                  // the streaming variant sets a function attribute at launch: captured lazily
+    for (int i = 0; i < 2; ++i) {
+        if (capture_two_steps(p, peer)) return -1;
+        p->cur ^= 1;                                 // the same two steps for the other buffer parity
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
 static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
 {
     cudaStream_t st = p->stream;
     const bool hooks = needs_hooks(p, mode);
-    if (launch == SAA_LAUNCH_AUTO) launch = (n_steps >= 8 ? SAA_LAUNCH_GRAPH : SAA_LAUNCH_PER_STEP);
+    if (launch == SAA_LAUNCH_AUTO) launch = (n_steps >= 2 ? SAA_LAUNCH_GRAPH : SAA_LAUNCH_PER_STEP);   // graphs exist since finalize
     if (hooks && launch == SAA_LAUNCH_PERSISTENT) return fail("history / prediction hooks are not available in the persistent loop");
     if (check_prediction(p, mode, n_steps)) return -1;
     if (hooks && launch == SAA_LAUNCH_GRAPH && n_steps >= 2) return step_hook_graph(p, n_steps, mode);
@@ -866,17 +907,7 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
     int64_t done = 0;
     if (launch == SAA_LAUNCH_GRAPH && n_steps >= 2) {
         const int c = p->cur;
-        if (!p->graph_exec[c]) {
-            cudaGraph_t g;
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int64_t l0 = p->launches;
-            launch_local_step(p, st);
-            launch_local_step(p, st);
-            p->launches = l0;
-            CK(cudaStreamEndCapture(st, &g));
-            CK(cudaGraphInstantiate(&p->graph_exec[c], g, 0));
-            CK(cudaGraphDestroy(g));
-        }
+        if (!p->graph_exec[c] && capture_two_steps(p, false)) return -1;
         for (; done + 2 <= n_steps; done += 2) {
             CK(cudaGraphLaunch(p->graph_exec[c], st));
             p->launches += 2;
@@ -893,10 +924,11 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
 }
 
 // one synchronised step of one plan, split in its three phases so that transports can interleave
+static inline bool use_peer(const saa_plan *p) { return p->peer && !(p->prefer_nccl && p->comm); }
 static void sync_phase_boundary(saa_plan *p, cudaStream_t st)
 {
     if (p->sh_slices > 0) {
-        if (p->peer)
+        if (use_peer(p))
             saa_k_boundary<true><<<nblk(p->sh_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(p->D, p->Hp, p->d_buf[p->cur], p->d_clk + p->cur);
         else
             saa_k_boundary<false><<<nblk(p->sh_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(p->D, p->H, p->d_buf[p->cur], p->d_clk + p->cur);
@@ -911,7 +943,7 @@ static void sync_phase_interior(saa_plan *p, cudaStream_t st)
 static void sync_phase_shared(saa_plan *p, cudaStream_t st)
 {
     if (p->sh_slices > 0) {
-        if (p->peer)
+        if (use_peer(p))
             saa_k_shared_update<true><<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur);
         else
             saa_k_shared_update<false><<<nblk(p->H.sh_rows, 256), 256, 0, st>>>(p->D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur);
@@ -947,10 +979,13 @@ static int step_sync_nccl(saa_plan *p, int64_t n_steps)
 static void launch_peer_step(saa_plan *p, cudaStream_t st)
 {
     if (p->peer_fused && p->sh_slices > 0) {
+        // shared rows go to the last blocks to finish (ticket), in units of 256 rows; at most two waiting blocks per SM
+        // (every schedule variant keeps >= 3 resident), so blocks that have not started always find a slot
         const unsigned n_main = nblk(p->n_slices, SAA_WARPS_PER_BLOCK);
-        const unsigned n_tail = nblk(p->H.sh_rows, 256);
-        launch_step_kernel(p->kvariant, n_main + n_tail, st, p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
-                           p->d_clk + (p->cur ^ 1), 0, n_main, 1u);
+        const unsigned n_units = nblk(p->H.sh_rows, 256);
+        const unsigned workers = std::max(1u, std::min(std::min(n_units, n_main), 2u * (unsigned)p->n_sms));
+        launch_step_kernel(p->kvariant, n_main, st, p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
+                           p->d_clk + (p->cur ^ 1), 0, workers, 1u);
         p->launches++;
         p->cur ^= 1;
         return;
@@ -968,17 +1003,7 @@ static int step_sync_peer(saa_plan *p, int64_t n_steps, int launch)
     if (hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) return step_hook_graph(p, n_steps, SAA_MODE_SYNC);
     if (!hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) {
         const int c = p->cur;
-        if (!p->graph_peer[c]) {
-            cudaGraph_t g;
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int64_t l0 = p->launches;
-            launch_peer_step(p, st);
-            launch_peer_step(p, st);
-            p->launches = l0;
-            CK(cudaStreamEndCapture(st, &g));
-            CK(cudaGraphInstantiate(&p->graph_peer[c], g, 0));
-            CK(cudaGraphDestroy(g));
-        }
+        if (!p->graph_peer[c] && capture_two_steps(p, true)) return -1;
         const int per = (p->sh_slices > 0 ? (p->peer_fused ? 1 : 3) : 1) * 2;
         for (; done + 2 <= n_steps; done += 2) {
             CK(cudaGraphLaunch(p->graph_peer[c], st));
@@ -1001,15 +1026,37 @@ extern "C" int saa_plan_step(saa_plan *p, int64_t n_steps, int mode, int launch)
     if (n_steps == 0) return 0;
     if (p->group) return fail("saa_plan_step: this plan belongs to a group; use saa_group_step");
     CK(cudaSetDevice(p->device));
+    p->state_epoch++;
     if (mode == SAA_MODE_LOCAL || mode == SAA_MODE_PREDICT) return step_local(p, n_steps, mode, launch);
     if (mode == SAA_MODE_SYNC) {
         if (p->size == 1) return step_local(p, n_steps, SAA_MODE_LOCAL, launch);   // Dynamic_solver.py:25 `if size != 1`
         if (p->group) return fail("saa_plan_step: this plan belongs to a group; use saa_group_step");
-        if (p->peer) return step_sync_peer(p, n_steps, launch);
+        if (p->peer && !(p->prefer_nccl && p->comm)) return step_sync_peer(p, n_steps, launch);
         if (!p->comm) return fail("saa_plan_step: SAA_MODE_SYNC needs a transport (saa_plan_peer_attach, saa_plan_init_nccl or saa_group_create)");
         return step_sync_nccl(p, n_steps);
     }
     return fail("saa_plan_step: unknown mode %d", mode);
+}
+
+extern "C" int saa_plan_set_option(saa_plan *p, int option, int value)
+{
+    NEED_FINAL(p, "saa_plan_set_option");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(plan_stream(p)));
+    if (option == SAA_OPT_PEER_FUSED) {
+        if ((value != 0) == p->peer_fused) return 0;
+        p->peer_fused = value != 0;
+        for (int i = 0; i < 2; ++i)
+            if (p->graph_peer[i]) { cudaGraphExecDestroy(p->graph_peer[i]); p->graph_peer[i] = nullptr; }
+        p->hook_epoch++;                                 // graphs of hooked synchronised steps hold the old form too
+        return p->peer ? prepare_graphs(p, true) : 0;
+    }
+    if (option == SAA_OPT_PREFER_NCCL) {
+        if (value && !p->comm) return fail("saa_plan_set_option: SAA_OPT_PREFER_NCCL needs saa_plan_init_nccl first");
+        p->prefer_nccl = value != 0;
+        return 0;
+    }
+    return fail("saa_plan_set_option: unknown option %d", option);
 }
 
 extern "C" int saa_plan_synchronize(saa_plan *p)
@@ -1025,21 +1072,31 @@ extern "C" int saa_plan_synchronize(saa_plan *p)
     return 0;
 }
 
-extern "C" int saa_step_host(saa_plan *p, const double *d0, const double *dn, double tn, int mode, double *d1)
+extern "C" int saa_step_host_ex(saa_plan *p, const double *d0, const double *dn, double tn, int mode, double *d1, int flags)
 {
     NEED_FINAL(p, "saa_step_host");
     if (!d0 || !dn || !d1) return fail("saa_step_host: null argument");
-    CK(cudaSetDevice(p->device));
-    cudaStream_t st = p->group ? p->group->stream : p->stream;
     if (p->group) return fail("saa_step_host: plan belongs to a group");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    // The reference's loop rotates d_n = d_0; d_0 = d1 (Data_prepare.py:233-234): the dn of this call is the d0 of the
+    // previous one, which the device still holds in the other displacement level (the step overwrote the OLD dn with
+    // d1 and swapped).  Valid only while nothing else touched the plan's state since that call.
+    const bool keep_dn = (flags & SAA_HOST_DN_IS_PREVIOUS_D0) && p->host_epoch == p->state_epoch;
     CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (set_state_from_stage(p, st, tn)) return -1;
+    if (!keep_dn) CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (set_state_from_stage(p, st, tn, !keep_dn)) return -1;
     if (saa_plan_step(p, 1, mode, SAA_LAUNCH_PER_STEP)) return -1;
     if (get_state_to_stage(p, st, true, false)) return -1;
     CK(cudaMemcpyAsync(d1, p->d_stage, p->n_dof * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    return 0;
+    p->host_epoch = p->state_epoch;
+    return keep_dn ? 1 : 0;
+}
+
+extern "C" int saa_step_host(saa_plan *p, const double *d0, const double *dn, double tn, int mode, double *d1)
+{
+    return saa_step_host_ex(p, d0, dn, tn, mode, d1, 0) < 0 ? -1 : 0;
 }
 
 // ---- caller-provided transport (MPI through mpi4py, gloo, ...): the messages pass through host memory ----
@@ -1061,6 +1118,7 @@ extern "C" int saa_plan_step_begin_host(saa_plan *p, double *send_host)
     NEED_FINAL(p, "saa_plan_step_begin_host");
     if (p->group) return fail("saa_plan_step_begin_host: plan belongs to a group");
     CK(cudaSetDevice(p->device));
+    p->state_epoch++;
     sync_phase_boundary(p, p->stream);
     if (p->total_msg > 0) {
         if (!send_host) return fail("saa_plan_step_begin_host: null send buffer");
@@ -1168,7 +1226,7 @@ extern "C" int saa_group_step(saa_group *g, int64_t n_steps, int mode, int launc
     CK(cudaSetDevice(g->plans[0]->device));
     cudaStream_t st = g->stream;
     // make sure earlier work on the plans' own streams (state uploads) is complete
-    for (saa_plan *p : g->plans) CK(cudaStreamSynchronize(p->stream));
+    for (saa_plan *p : g->plans) { CK(cudaStreamSynchronize(p->stream)); p->state_epoch++; }
     for (int64_t s = 0; s < n_steps; ++s) {
         if (mode == SAA_MODE_SYNC && g->plans.size() > 1) {
             for (saa_plan *p : g->plans) sync_phase_boundary(p, st);
@@ -1239,7 +1297,7 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
     if (n_nb != (int)p->nb_rank.size()) return fail("saa_plan_peer_attach: %d handles for %d neighbours", n_nb, (int)p->nb_rank.size());
     if (p->peer) return fail("saa_plan_peer_attach: already attached");
     if (n_nb > 255) return fail("saa_plan_peer_attach: more than 255 neighbours");
-    if (n_nb == 0) { p->peer = true; p->Hp = p->H; return 0; }
+    if (n_nb == 0) { p->peer = true; p->Hp = p->H; return prepare_graphs(p, true); }
     if (!handles64 || !remote_off || !remote_total || !remote_slot || !remote_n_nb) return fail("saa_plan_peer_attach: null argument");
     CK(cudaSetDevice(p->device));
     std::vector<double *> recv(n_nb);
@@ -1249,9 +1307,10 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
         cudaIpcMemHandle_t h;
         memcpy(&h, (const char *)handles64 + 64 * k, sizeof h);
         void *ptr = nullptr;
-        if (getenv("SAA_DEBUG_PEER_SELF")) {
-            ptr = p->d_recv;                          // single-GPU timing probe: "the neighbour" is this plan itself
-        } else {
+#ifdef SAA_DEBUG_PEER
+        if (getenv("SAA_DEBUG_PEER_SELF")) ptr = p->d_recv;   // single-GPU timing probe: "the neighbour" is this plan itself
+#endif
+        if (!ptr) {
             CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
             p->peer_mapped.push_back(ptr);
         }
@@ -1274,10 +1333,18 @@ extern "C" int saa_plan_peer_attach(saa_plan *p, int n_nb, const void *handles64
     p->Hp.peer_recv = p->d_peer_recv; p->Hp.peer_stride = p->d_peer_stride; p->Hp.peer_flag = p->d_peer_flag;
     const char *fz = getenv("SAA_PEER_FUSED");
     p->peer_fused = !(fz && fz[0] == '0');
-    const char *dbg = getenv("SAA_DEBUG_PEER");        // timing experiments only: results are wrong when set
-    p->Hp.dbg = dbg ? atoi(dbg) : 0;
+    p->Hp.dbg = 0;
+#ifdef SAA_DEBUG_PEER                                  // profiling builds only (make DEBUG_PEER=1): results are wrong when set
+    if (const char *dbg = getenv("SAA_DEBUG_PEER")) {
+        p->Hp.dbg = atoi(dbg);
+        fprintf(stderr, "[saa] SAA_DEBUG_PEER=%d: timing experiment, RESULTS ARE WRONG\n", p->Hp.dbg);
+    }
+#else
+    if (getenv("SAA_DEBUG_PEER") || getenv("SAA_DEBUG_PEER_SELF"))
+        return fail("saa_plan_peer_attach: SAA_DEBUG_PEER* is set but this library was built without -DSAA_DEBUG_PEER");
+#endif
     p->peer = true;
-    return 0;
+    return prepare_graphs(p, true);
 }
 
 // ---- NCCL transport -----------------------------------------------------------------------------------------

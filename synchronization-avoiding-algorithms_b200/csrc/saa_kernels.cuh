@@ -91,8 +91,9 @@ struct SaaHaloDev {
     unsigned int *done_ctr;                 // blocks of the pack kernel that have finished (last one raises the flags)
     unsigned long long *own_ready;          // fused step: number of steps whose own boundary forces are complete
     unsigned int *err;                      // set when a bounded wait expired (a peer never delivered)
-    int dbg;                                // timing experiments only (SAA_DEBUG_PEER): 1 no waits, 2 local stores,
-                                            // 4 skip the tail blocks, 8 treat boundary slices as interior
+    unsigned int *tail_ticket;              // fused step: blocks that have finished their slices (the last ones take the shared rows)
+    int dbg;                                // -DSAA_DEBUG_PEER builds only (timing experiments): 1 no waits, 2 local stores,
+                                            // 4 skip the shared rows, 8 treat boundary slices as interior
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
@@ -408,21 +409,29 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
 }
 
 // THE step kernel.  Local steps and the interior phase of the staged transports run it with sh_slices = 0 and
-// no tail blocks (pure K1 over slices [slice_begin, n_slices)).  With the peer transport it is K1+K2+K3 in ONE
-// launch per synchronised step: blocks are dispatched in index order, so
-//   * the first blocks own the boundary slices (internal order is boundary-first): partial forces -> own buffer
-//     and straight into the neighbours' receive areas; the warp that completes the last boundary slice raises
-//     the neighbours' arrival flags (system scope) and the local "own forces ready" flag;
-//   * the bulk of the grid streams the interior slices exactly like saa_k_step<true>, overlapping the NVLink
-//     traffic;
-//   * the last few blocks (index >= n_main) wait for the arrival flags, then do the rank-ordered sum and the
-//     update of the shared rows.
+// tail_workers = 0 (pure K1 over slices [slice_begin, n_slices)).  With the peer transport it is K1+K2+K3 in ONE
+// launch per synchronised step:
+//   * the blocks owning the boundary slices (internal order is boundary-first, so these are the lowest block
+//     indices, which the hardware dispatches first): partial forces -> own buffer and straight into the
+//     neighbours' receive areas; the warp that completes the last boundary slice raises the neighbours' arrival
+//     flags (system scope) and the local "own forces ready" flag;
+//   * the bulk of the grid streams the interior slices, overlapping the NVLink traffic;
+//   * every block takes a ticket when it has FINISHED its slices; the last `tail_workers` finishers wait for the
+//     arrival flags, then do the rank-ordered sum and the update of the shared rows (units of 256 rows, strided
+//     over the workers).  Correctness does not depend on the order in which blocks are dispatched: waiting blocks
+//     have no slices left, and at most tail_workers (< resident capacity of the GPU) of them exist, so every
+//     block that has not run yet always finds a free slot.
 // Same arithmetic, same order as the three-kernel sequence — one launch gap and no pipeline drain per step.
 //   count_sync: 1 on synchronised steps (advances the exchange counter), 0 on local ones.
+#ifdef SAA_DEBUG_PEER          // timing experiments only (profiling builds): results are WRONG when H.dbg != 0
+#define SAA_DBG(H, bit) ((H).dbg & (bit))
+#else
+#define SAA_DBG(H, bit) 0
+#endif
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
                                                         double *__restrict__ dn_d1, const SaaClock *clk_in, SaaClock *clk_out,
-                                                        int64_t slice_begin, unsigned int n_main, unsigned int count_sync)
+                                                        int64_t slice_begin, unsigned int tail_workers, unsigned int count_sync)
 {
     const unsigned long long step = clk_in->sync_step;
     const double tn = clk_in->tn;
@@ -431,56 +440,67 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
         clk_out->sync_step = step + count_sync;
         clk_out->step_idx = clk_in->step_idx + 1ull;
     }
-    if (blockIdx.x < n_main) {
+    {
         const int lane = threadIdx.x & 31;
         const int64_t slice = slice_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (slice >= P.n_slices) return;
-        double s[3];
-        saa_node_dot<MODE, true>(P, slice, lane, d0, s);
-        if (slice < P.sh_slices && !(H.dbg & 8)) {
+        if (slice < P.n_slices) {
+            double s[3];
+            saa_node_dot<MODE, true>(P, slice, lane, d0, s);
+            if (slice < P.sh_slices && !SAA_DBG(H, 8)) {
 #pragma unroll
-            for (int A = 0; A < 3; ++A) {
-                const int64_t row = 3 * (slice * 32 + lane) + A;
-                H.xbuf[row] = s[A];
-                for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
-                    const int nb = H.dst_nb[k];
-                    if (H.dbg & 2) H.sendbuf[H.dst_pos[k] % 3] = s[A];
-                    else H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
+                for (int A = 0; A < 3; ++A) {
+                    const int64_t row = 3 * (slice * 32 + lane) + A;
+                    H.xbuf[row] = s[A];
+                    for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+                        const int nb = H.dst_nb[k];
+                        if (SAA_DBG(H, 2)) H.sendbuf[H.dst_pos[k] % 3] = s[A];
+                        else H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
+                    }
                 }
-            }
-            if (!(H.dbg & 2)) __threadfence_system();
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned int t = atomicAdd(H.done_ctr, 1u);
-                if (t == (unsigned int)P.sh_slices - 1u) {
-                    *H.done_ctr = 0u;
-                    __threadfence_system();
-                    for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
-                    st_release_gpu_u64(H.own_ready, step + 1ull);
+                if (!SAA_DBG(H, 2)) __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned int t = atomicAdd(H.done_ctr, 1u);
+                    if (t == (unsigned int)P.sh_slices - 1u) {
+                        *H.done_ctr = 0u;
+                        __threadfence_system();
+                        for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
+                        st_release_gpu_u64(H.own_ready, step + 1ull);
+                    }
                 }
+            } else {
+                saa_finish_node<true>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
             }
-        } else {
-            saa_finish_node<true>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
         }
-        return;
     }
-    // tail blocks: shared rows
-    if (H.dbg & 4) return;
-    if (!(H.dbg & 1)) {
+    if (tail_workers == 0u) return;                   // local step / interior phase: no shared rows in this launch
+    // ---- shared rows: the last `tail_workers` blocks to finish their slices
+    __shared__ unsigned int s_ticket;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(H.tail_ticket, 1u);
+        if (t == gridDim.x - 1u) *H.tail_ticket = 0u; // last ticket of this launch: re-arm (the next launch is stream-ordered)
+        s_ticket = t;
+    }
+    __syncthreads();
+    const unsigned int first = gridDim.x - tail_workers;
+    if (s_ticket < first || SAA_DBG(H, 4)) return;
+    if (!SAA_DBG(H, 1)) {
         if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
         if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
     }
     __syncthreads();
     const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
-    const int64_t row = (int64_t)(blockIdx.x - n_main) * blockDim.x + threadIdx.x;
-    if (row >= H.sh_rows) return;
-    double Fi = 0.0;
-    for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
-        const int32_t q = H.src_pos[k];
-        const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
-        Fi = __dadd_rn(Fi, v);
+    const double ramp = saa_ramp(tn);
+    for (int64_t row = (int64_t)(s_ticket - first) * blockDim.x + threadIdx.x; row < H.sh_rows; row += (int64_t)tail_workers * blockDim.x) {
+        double Fi = 0.0;
+        for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+            const int32_t q = H.src_pos[k];
+            const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
+            Fi = __dadd_rn(Fi, v);
+        }
+        saa_finish_row(P, row, Fi, d0, dn_d1, ramp);
     }
-    saa_finish_row(P, row, Fi, d0, dn_d1, saa_ramp(tn));
 }
 
 // ---------------------------------------------------------------------------------------------------

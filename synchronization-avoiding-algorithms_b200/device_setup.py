@@ -71,6 +71,52 @@ def structured_slab_cells(m, rank, size, length=25, device="cuda"):
     return nid.reshape(-1, 4)
 
 
+def block_grid(size):
+    """Process grid (px, py, pz) of the block partition: cuts along x first, then y, then z (8 -> 2 x 2 x 2, so that a
+    rank has up to 7 neighbours and edges / the centre line of the beam are held by 4 / 8 ranks)."""
+    g = [1, 1, 1]
+    ax, left = 0, int(size)
+    while left > 1:
+        if left % 2:
+            raise ValueError("block partition needs a power-of-two number of ranks")
+        g[ax % 3] *= 2
+        ax += 1
+        left //= 2
+    return tuple(g)
+
+
+def structured_block_cells(m, rank, size, length=25, grid=None, device="cuda"):
+    """Same as structured_slab_cells for a px x py x pz block partition of the hexahedra (rank = (bx*py + by)*pz + bz):
+    this rank's elements in ascending global element order."""
+    import torch
+    nx, ny, nz = mesh.structured_beam_dims(m, length)
+    px, py, pz = grid or block_grid(size)
+    if px * py * pz != size:
+        raise ValueError(f"block grid {px}x{py}x{pz} does not match {size} ranks")
+    bz, by, bx = rank % pz, (rank // pz) % py, rank // (pz * py)
+    rng = lambda n, p, b: ((b * n) // p, ((b + 1) * n) // p)
+    (x0, x1), (y0, y1), (z0, z1) = rng(nx, px, bx), rng(ny, py, by), rng(nz, pz, bz)
+    kuhn = torch.as_tensor(mesh._KUHN, device=device)
+    ix = torch.arange(x0, x1, device=device, dtype=torch.int64)
+    iy = torch.arange(y0, y1, device=device, dtype=torch.int64)
+    iz = torch.arange(z0, z1, device=device, dtype=torch.int64)
+    IX, IY, IZ = torch.meshgrid(ix, iy, iz, indexing="ij")               # lexicographic = ascending global hexahedron id
+    IX, IY, IZ = IX.reshape(-1, 1, 1), IY.reshape(-1, 1, 1), IZ.reshape(-1, 1, 1)
+    nid = ((IX + kuhn[None, :, :, 0]) * (ny + 1) + (IY + kuhn[None, :, :, 1])) * (nz + 1) + (IZ + kuhn[None, :, :, 2])
+    return nid.reshape(-1, 4)
+
+
+def block_partition(m, size, length=25, grid=None):
+    """epart (host, int64) of mesh.structured_beam(m) for the block partition — for tests / small meshes."""
+    nx, ny, nz = mesh.structured_beam_dims(m, length)
+    px, py, pz = grid or block_grid(size)
+    h = np.arange(nx * ny * nz, dtype=np.int64)
+    iz, iy, ix = h % nz, (h // nz) % ny, h // (nz * ny)
+    own = lambda i, n, p: np.minimum(((i + 1) * p - 1) // n, p - 1)    # block b owns [b*n//p, (b+1)*n//p)
+    r = (own(ix, nx, px) * py + own(iy, ny, py)) * pz + own(iz, nz, pz)
+    return np.repeat(r, 6)
+
+
 def structured_points(m, node_ids, length=25):
     """Coordinates (n,3) float64 of the given global node ids of mesh.structured_beam(m) (device tensor)."""
     import torch
@@ -256,12 +302,18 @@ def rank_local(cells_global, points_of, clamped_of, rank, size, device_index=0, 
                 dirichlet=maps.node_to_dof(3, [0, 1, 2], clamped), n_global_nodes=n_global_nodes, n_global_elem=n_global_elem)
 
 
-def structured_rank_local(m, rank, size, device_index=0, length=25, **kw):
-    """Phase 1 for the structured cantilever: x-slab `rank` of `size`, generated on the device."""
+def structured_rank_local(m, rank, size, device_index=0, length=25, partition="slabs", grid=None, **kw):
+    """Phase 1 for the structured cantilever, generated on the device: x-slab `rank` of `size` (partition="slabs")
+    or block `rank` of a px x py x pz grid (partition="blocks")."""
     import torch
     dev = torch.device("cuda", device_index)
     nx, ny, nz = mesh.structured_beam_dims(m, length)
-    cells_g = structured_slab_cells(m, rank, size, length, device=dev)
+    if partition == "blocks":
+        cells_g = structured_block_cells(m, rank, size, length, grid, device=dev)
+    elif partition == "slabs":
+        cells_g = structured_slab_cells(m, rank, size, length, device=dev)
+    else:
+        raise ValueError(f"unknown structured partition {partition!r}")
     return rank_local(cells_g, lambda ids: structured_points(m, ids, length), lambda ids: ids < (ny + 1) * (nz + 1), rank, size,
                       device_index, n_global_nodes=(nx + 1) * (ny + 1) * (nz + 1), n_global_elem=6 * nx * ny * nz, **kw)
 

@@ -98,7 +98,7 @@ def structured_beam_dims(m, length=25):
     return nx, ny, nz
 
 
-def structured_beam(m, length=25, dtype_index=np.int64, with_facets="x0"):
+def structured_beam(m, length=25, dtype_index=np.int64, with_facets="x0", nx=None):
     """25 x 1 x 1 cantilever as (25m) x m x m hexahedra -> 6 Kuhn tets each.
 
     Node id is lexicographic with z fastest, then y, x slowest: id = (ix*(ny+1)+iy)*(nz+1)+iz, so
@@ -108,7 +108,8 @@ def structured_beam(m, length=25, dtype_index=np.int64, with_facets="x0"):
     with_facets: "x0" -> only the boundary triangles on the clamped face x=0 (all that
     Data_prepare.py:127-135 looks at); "all" -> the whole boundary surface; None -> no facets.
     """
-    nx, ny, nz = structured_beam_dims(m, length)
+    nx_full, ny, nz = structured_beam_dims(m, length)
+    nx = nx_full if nx is None else int(nx)          # nx: only the first nx hexahedron layers (a slab sample of the beam)
     h = 1.0 / m
     gx = np.arange(nx + 1, dtype=np.float64) * h
     gy = np.arange(ny + 1, dtype=np.float64) * h

@@ -23,6 +23,8 @@ _lib = None
 
 MODE_LOCAL, MODE_SYNC, MODE_PREDICT = 0, 1, 2
 LAUNCH_AUTO, LAUNCH_PER_STEP, LAUNCH_GRAPH, LAUNCH_PERSISTENT = 0, 1, 2, 3
+HOST_DN_IS_PREVIOUS_D0 = 1
+OPT_PEER_FUSED, OPT_PREFER_NCCL = 1, 2
 
 # every symbol include/saa_fem.h declares: name -> (restype, argtypes)
 _vp, _i64, _i32, _f64, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_int
@@ -52,8 +54,10 @@ ABI = {
     "saa_plan_get_state_dev": (_int, [_vp, _vp, _vp, _vp]),
     "saa_plan_step": (_int, [_vp, _i64, _int, _int]),
     "saa_plan_synchronize": (_int, [_vp]),
+    "saa_plan_set_option": (_int, [_vp, _int, _int]),
     "saa_plan_stream": (_vp, [_vp]),
     "saa_step_host": (_int, [_vp, _vp, _vp, _f64, _int, _vp]),
+    "saa_step_host_ex": (_int, [_vp, _vp, _vp, _f64, _int, _vp, _int]),
     "saa_plan_set_history": (_int, [_vp, _vp, _i64, _i64, _i64]),
     "saa_plan_history_count": (_i64, [_vp]),
     "saa_plan_read_history": (_int, [_vp, _i64, _i64, _vp]),
@@ -267,14 +271,32 @@ class StepPlan:
     def synchronize(self):
         _check(lib().saa_plan_synchronize(self.h), "saa_plan_synchronize")
 
+    def set_option(self, option, value):
+        _check(lib().saa_plan_set_option(self.h, int(option), int(value)), "saa_plan_set_option")
+
     def step_host(self, d0, dn, tn, mode=MODE_LOCAL, out=None):
-        """One parallel_explicit_solver_dis_pre evaluation with host buffers -> d1 (n_dof,)."""
+        """One parallel_explicit_solver_dis_pre evaluation with host buffers -> d1 (n_dof,).
+
+        The reference's loop rotates `d_n = d_0; d_0 = d1` (Data_prepare.py:233-234), so the `dn` of a call is
+        normally the very array passed as `d0` to the previous call; its values are still on the device and are not
+        uploaded again (saa_step_host_ex, SAA_HOST_DN_IS_PREVIOUS_D0).  "The very array" = same memory, kept alive
+        by this plan since the previous call.  Writing INTO that array between the two calls is not detected — the
+        reference never does (it only writes into the returned d1, Online_predictor.py:298, which is always
+        uploaded); set SAA_STEP_HOST_FULL_UPLOAD=1 to upload both vectors on every call."""
         d0 = np.ascontiguousarray(d0, dtype=np.float64).reshape(-1)
         dn = np.ascontiguousarray(dn, dtype=np.float64).reshape(-1)
         if d0.size != self.n_dof or dn.size != self.n_dof:
             raise SaaError("step_host: wrong vector length")
         d1 = np.empty(self.n_dof) if out is None else out
-        _check(lib().saa_step_host(self.h, _p(d0), _p(dn), float(tn), int(mode), _p(d1)), "saa_step_host")
+        prev = getattr(self, "_host_prev_d0", None)
+        flags = 0
+        if prev is not None and prev.ctypes.data == dn.ctypes.data and not os.environ.get("SAA_STEP_HOST_FULL_UPLOAD"):
+            flags = HOST_DN_IS_PREVIOUS_D0
+        rc = lib().saa_step_host_ex(self.h, _p(d0), _p(dn), float(tn), int(mode), _p(d1), flags)
+        if rc < 0:
+            _check(rc, "saa_step_host_ex")
+        self._host_prev_d0 = d0                      # keeps the memory alive: the same address next time is the same array
+        self.host_uploads_skipped = getattr(self, "host_uploads_skipped", 0) + (1 if rc == 1 else 0)
         return d1
 
     # ---- history / prediction ----------------------------------------------------------------------

@@ -52,7 +52,9 @@ class SyncAvoidingRun:
         self.block = self.n_f * self.n_s
         self.tables = [] if keep_tables else None
         self.t_predict = 0.0                                                   # wall seconds spent in LSTM inference
-        self._live = []                                                        # tables referenced by the plans
+        self.n_predict = 0                                                     # refill inferences so far
+        self._live = []                                                        # tables of the refill block in progress (referenced by the plans)
+        self._blk_start = 0                                                    # step index that took row 0 of those tables
         cap = self.n_p * self.n_s + self.block
         for pl, d in zip(self.plans, self.dofs):
             pl.set_history(d, capacity=cap, save_every=1)
@@ -79,36 +81,38 @@ class SyncAvoidingRun:
         return out
 
     def run(self, test_num):
-        """advance to step index `test_num` (exclusive), like `while i < test_num` of Online_predictor.py:251"""
-        torch = self.torch
+        """advance to step index `test_num` (exclusive), like `while i < test_num` of Online_predictor.py:251.
+
+        May be called repeatedly with growing `test_num` (e.g. once per saved step): the refill block in progress —
+        its prediction tables, its first step (the reference's `i` at :280) and the rows already consumed (the
+        reference's counter2, :284-316) — is kept between calls, so a chunked run performs exactly the same
+        inferences and uses exactly the same table rows as a single `run(T)`."""
+        import time as _time
         while self.i < test_num:
             if self.i <= self.i_cri:                                           # phase 1: synchronised
                 n = min(test_num, self.i_cri + 1) - self.i
                 self.stepper.step(n, _plan.MODE_SYNC)
                 self.i += n
                 continue
-            import time as _time
-            for pl in self.plans:
-                pl.synchronize()
-            _t0 = _time.perf_counter()
-            tables = self._predict_tables()                                    # :280
-            self.t_predict += _time.perf_counter() - _t0
-            if self.tables is not None:
-                self.tables.append([t.cpu().numpy() for t in tables])
-            self._live = tables
-            for pl, d, t in zip(self.plans, self.dofs, tables):
-                # the DOF list is handed over once; afterwards only the table changes (keeps the plan's step graphs valid)
-                pl.set_prediction(None if getattr(pl, "_sa_dofs_set", False) else d, t.data_ptr(), t.shape[0])
-                pl._sa_dofs_set = True
-            n_blk = min(self.block, test_num - self.i)
-            done = 0
+            done = self.i - self._blk_start if self._live else self.block     # rows of the current block already used
+            if done >= self.block:                                             # block boundary: new inference (:280)
+                for pl in self.plans:
+                    pl.synchronize()
+                _t0 = _time.perf_counter()
+                tables = self._predict_tables()
+                self.t_predict += _time.perf_counter() - _t0
+                self.n_predict += 1
+                if self.tables is not None:
+                    self.tables.append([t.cpu().numpy() for t in tables])
+                self._live, self._blk_start, done = tables, self.i, 0
+            tables = self._live
+            self._point_plans_at(done)
+            n_blk = min(self.block, done + (test_num - self.i))
             while done < n_blk:                                                # :284-316
                 if self.k and (self.i % self.k == 0):
                     # true exchange on this step; its table row is skipped
                     self.stepper.step(1, _plan.MODE_SYNC)
-                    for pl, d, t in zip(self.plans, self.dofs, tables):
-                        rest = t[done + 1:]
-                        pl.set_prediction(None, rest.data_ptr() if rest.shape[0] else t.data_ptr(), rest.shape[0])
+                    self._point_plans_at(done + 1)
                     seg = 1
                 else:
                     nxt = n_blk - done
@@ -121,3 +125,12 @@ class SyncAvoidingRun:
             for pl in self.plans:
                 pl.synchronize()
         return self.i
+
+    def _point_plans_at(self, row):
+        """the next SAA_MODE_PREDICT step of every plan takes row `row` of the current block's table"""
+        for pl, d, t in zip(self.plans, self.dofs, self._live):
+            rest = t[row:]
+            # the DOF list is handed over once; afterwards only the table changes (keeps the plan's step graphs valid)
+            pl.set_prediction(None if getattr(pl, "_sa_dofs_set", False) else d, rest.data_ptr() if rest.shape[0] else t.data_ptr(),
+                              rest.shape[0])
+            pl._sa_dofs_set = True

@@ -242,23 +242,125 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
-@pytest.mark.parametrize("name,n", [("beam_coarse_P2", 2), ("beam_coarse_P4", 4), ("beam_coarse_P8", 8)])
-def test_one_process_per_gpu_transports(transport, name, n):
-    """N GPUs of one box, one process each: NVLink peer-memory stores / NCCL send-recv reproduce the
-    reference's syn_cpus histories bit for bit (skipped when the box has fewer GPUs)."""
+def _run_workers(transport, name, n, timeout=600):
     import os
     import subprocess
     import sys
-    if _ngpu() < n:
-        pytest.skip(f"needs {n} GPUs")
     from util import ROOT
-    port = 29600 + (os.getpid() + 13 * n) % 300
+    port = 29600 + (os.getpid() + 13 * n + len(name)) % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), transport, name]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(f"ok ({transport})") == n
+
+
+def _have_mid(n):
+    import os
+    from util import GOLDEN
+    return os.path.isfile(os.path.join(GOLDEN, f"mid_m8_np{n}.npz"))
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("name,n", [("beam_coarse_P2", 2), ("beam_coarse_P4", 4), ("beam_coarse_P8", 8),
+                                    ("mid_m8_np2", 2), ("mid_m8_np4", 4), ("mid_m8_np8", 8)])
+def test_one_process_per_gpu_transports(transport, name, n):
+    """N GPUs of one box, one process each: NVLink peer-memory stores (fused single-launch step and its three-kernel
+    form) / NCCL send-recv reproduce the reference's syn_cpus histories bit for bit (skipped when the box has fewer
+    GPUs).  mid_*: 48 843 DOF in METIS partitions — several boundary slices and shared-row units per rank."""
+    if _ngpu() < n:
+        pytest.skip(f"needs {n} GPUs")
+    if name.startswith("mid_") and not _have_mid(n):
+        pytest.skip("mid-size fixture not generated")
+    _run_workers(transport, name, n)
+
+
+def test_fused_peer_step_two_processes_sharing_this_gpu():
+    """The fused peer-memory step (the kernel behind every multi-GPU number) on a ONE-GPU box: two processes share the
+    device, map each other's receive areas through CUDA IPC exactly as on two GPUs, and their kernels time-slice.  The
+    golden histories of the unmodified reference must come out bit for bit."""
+    _run_workers("peer", "beam_coarse_P2", 2, timeout=420)
+
+
+def test_mid_fixture_is_reproducible():
+    """tests/golden/mid_m8_np*.npz were produced on another B200 box by oracle/gen_golden_mid.py (device assembly -> CPU
+    oracle).  Regenerating them here must give the same bits (deterministic device assembly, same METIS partition), and
+    the CUDA group run on those matrices must reproduce them."""
+    import os
+    import sys
+    from util import GOLDEN, ROOT
+    if not _have_mid(4):
+        pytest.skip("mid-size fixture not generated")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden_mid
+    from saa_b200 import device_setup
+    for P in (4, 8):
+        z = np.load(os.path.join(GOLDEN, f"mid_m8_np{P}.npz"))
+        g = gen_golden_mid.generate(P)
+        assert np.array_equal(g["epart"], z["epart"])
+        for s in (int(x) for x in z["steps"]):
+            for q in range(P):
+                assert bits_equal(g[f"hist_{s}_r{q}"], z[f"hist_{s}_r{q}"]), (P, s, q)
+        pts, cells, fac = mesh.structured_beam(int(z["m"]))
+        plans, infos = device_setup.build_mesh_in_process(pts, cells, fac, z["epart"].astype(np.int64), P)
+        grp = splan.PlanGroup(plans)
+        done = 0
+        for s in (int(x) for x in z["steps"]):
+            grp.step(s - done, splan.MODE_SYNC)
+            grp.synchronize()
+            done = s
+            for q in range(P):
+                assert bits_equal(plans[q].d0(), z[f"hist_{s}_r{q}"]), (P, s, q)
+        assert int(z["stats"][2]) > 0                       # nodes held by three or more ranks exist
+
+
+def test_step_host_skips_the_dn_upload_only_for_the_rotated_array():
+    """saa_step_host_ex: the loop of Data_prepare.py:223-235 with host arrays — the dn of a call is the d0 array of the
+    previous one and is not uploaded again; the results equal the oracle bit for bit.  A different array, or any other
+    plan call in between, forces the full upload; SAA_STEP_HOST_FULL_UPLOAD=1 disables the hint."""
+    import os
+    g = load_golden("beam_coarse_P1")
+    pl = golden_plans_single(g, 0)
+    o = make_oracle(g)
+    n = pl.n_dof
+    d_0, d_n, tn = np.zeros(n), np.zeros(n), 0
+    for i in range(40):
+        d1 = pl.step_host(d_0, d_n, tn, splan.MODE_LOCAL)
+        d_n = d_0
+        d_0 = d1
+        tn = tn + g["dt"]
+    o.run(40)
+    assert bits_equal(d_0, o.d0(0))
+    assert pl.host_uploads_skipped == 39
+    # the caller edits the returned d1 (Online_predictor.py:298 does): always uploaded
+    d_0[5] = 1e-3
+    d1 = pl.step_host(d_0, d_n, tn, splan.MODE_LOCAL)
+    assert pl.host_uploads_skipped == 40
+    e0, en, etn = o.state(0)
+    e0[5] = 1e-3
+    o.set_state(0, e0, en, etn)
+    o.run(1, model=True)
+    assert bits_equal(d1, o.d0(0))
+    # a dn that is NOT the previous d0 array (a copy): full upload, same result as a fresh plan
+    d1b = pl.step_host(d1, d_0.copy(), tn, splan.MODE_LOCAL)
+    assert pl.host_uploads_skipped == 40
+    # another plan call in between invalidates the resident copy even when the array is the rotated one
+    pl.step(1, splan.MODE_LOCAL)
+    d1c = pl.step_host(d1b, d1, tn, splan.MODE_LOCAL)
+    assert pl.host_uploads_skipped == 40
+    fresh = golden_plans_single(g, 0)
+    assert bits_equal(d1c, fresh.step_host(d1b, d1, tn, splan.MODE_LOCAL))
+    # documented limit: writing INTO the previous d0 array between calls is not seen unless the hint is switched off
+    d1d = pl.step_host(d1c, d1b, tn, splan.MODE_LOCAL)
+    assert pl.host_uploads_skipped == 41
+    os.environ["SAA_STEP_HOST_FULL_UPLOAD"] = "1"
+    try:
+        d1c[:] = 0.0
+        got = pl.step_host(d1d, d1c, tn, splan.MODE_LOCAL)
+        assert pl.host_uploads_skipped == 41
+        assert bits_equal(got, fresh.step_host(d1d, np.zeros(n), tn, splan.MODE_LOCAL))
+    finally:
+        del os.environ["SAA_STEP_HOST_FULL_UPLOAD"]
 
 
 def test_malformed_matrices_are_rejected_and_plans_can_be_recycled():

@@ -311,3 +311,44 @@ def test_sync_avoiding_trajectory_of_the_reference_on_gpu():
         assert np.abs(H - z[f"d_sol_r{q}"][T - cap:]).max() <= 5e-5 * span
         ref = z[f"final_r{q}"]
         assert np.linalg.norm(plans[q].d0() - ref) <= 2e-4 * np.linalg.norm(ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resync", [None, 7])
+def test_chunked_sync_avoiding_run_equals_single_run(resync):
+    """SyncAvoidingRun.run(i + 1) once per step (what a driver that saves every step does) == one run(T): the refill
+    block in progress survives between calls — same number of inferences, same table rows, same bits."""
+    import scipy.sparse as sp
+    import saa_b200  # noqa: F401
+    from saa_b200 import maps, plan as splan, sync_avoiding
+    z, g, models = _online_golden()
+    n_p, n_f, n_s, T = int(z["n_p"]), int(z["n_f"]), int(z["n_s"]), int(z["test_num"])
+    smax, smin = float(z["scale_max"]), float(z["scale_min"])
+    lists = [r["nodes"] for r in g["ranks"]]
+    outs = []
+    for chunked in (False, True):
+        plans = []
+        for q, r in enumerate(g["ranks"]):
+            n = r["F"].size
+            K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+            plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), halo=maps.halo_plan(q, 2, lists), rank=q, size=2))
+        grp = splan.PlanGroup(plans)
+        run = sync_avoiding.SyncAvoidingRun(plans, grp, [r["loc_dof_shared"] for r in g["ranks"]], models, [(smax, smin)] * 2, n_p, n_f, n_s,
+                                            resync_every=resync, keep_tables=True)
+        if chunked:
+            for i in range(T):
+                run.run(i + 1)
+        else:
+            run.run(T)
+        grp.synchronize()
+        cap = n_p * n_s + n_f * n_s
+        outs.append(([p.d0() for p in plans], [p.read_history(T - cap, cap) for p in plans], run.n_predict, run.tables))
+    assert outs[0][2] == outs[1][2] == -(-(T - n_p * n_s) // (n_f * n_s))
+    for q in range(2):
+        assert bits_equal(outs[0][0][q], outs[1][0][q]) and bits_equal(outs[0][1][q], outs[1][1][q])
+        for a, b in zip(outs[0][3], outs[1][3]):
+            assert bits_equal(a[q], b[q])
+    if resync is None:                                   # and both follow the reference's own loop (golden trajectory)
+        span = smax - smin
+        for q in range(2):
+            assert np.abs(outs[1][1][q] - z[f"d_sol_r{q}"][T - cap:]).max() <= 5e-5 * span

@@ -53,3 +53,21 @@ def test_oracle_csr_matvec_is_scipy_order():
     x = rng.standard_normal((2000, 1))
     y = oracle_module().csr_matvec(A.indptr, A.indices, A.data, x)
     assert bits_equal(y, A.dot(x))
+
+
+@pytest.mark.parametrize("name,model", [("beam_coarse_P1", False), ("beam_coarse_P2", False), ("beam_coarse_P3", False), ("beam_coarse_P2", True)])
+def test_numpy_step_baseline_matches_reference_histories_bitwise(name, model):
+    """oracle/numpy_step.py — the reference's numpy/scipy statement sequence on P single-threaded processes (the
+    numpy-scipy CPU baseline of bench.py) — reproduces the golden histories of the unmodified reference."""
+    import os
+    import sys
+    from util import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy_step
+    g = load_golden(name)
+    steps = [int(s) for s in (g["nosync_steps"] if model else g["steps"])]
+    n = [s for s in steps if s <= 100][-1]
+    secs, states = numpy_step.run_ranks(g["ranks"], len(g["points"]), g["dt"], float(g["alpha"]), n, model=model, want_state=True)
+    for q in range(g["P"]):
+        assert bits_equal(states[q], g[f"{'nosync' if model else 'hist'}_{n}_r{q}"]), (name, q)
+    assert secs > 0
