@@ -59,6 +59,10 @@ def parse():
     ap.add_argument("--partition", default="slabs", choices=["slabs", "blocks", "metis"],
                     help="N > 1: x-slabs of whole hexahedron layers, a px x py x pz block grid (8 -> 2x2x2), or METIS_PartMeshDual "
                          "(host mesh, m <= 27)")
+    ap.add_argument("--blocks", default="", help="--partition blocks: the process grid PXxPYxPZ (default: cuts along x, then y, then z)")
+    ap.add_argument("--kernel", default="assembled", choices=["assembled", "matfree"],
+                    help="matfree (one GPU): kernel K5, f_int = sum_e B^T D B u_e evaluated element by element, node-owned accumulation — a "
+                         "throughput / low-memory mode reported with its own roofline and its measured difference from the assembled path")
     ap.add_argument("--cpu-seconds", type=float, default=0.0, help="CPU time budget per baseline (0: 10 s native arm, 15 s reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra measurements of the other BASELINE configs")
@@ -166,7 +170,7 @@ def setup_host(m, size, rank, local, make_plan=True, nx=None, all_ranks=False, e
                     assembly="host (numpy/scipy, bit-exact with the reference's assembly)")
 
 
-def setup_device(m, size, rank, local, partition="slabs"):
+def setup_device(m, size, rank, local, partition="slabs", grid=None, keep_mesh=False):
     """Device set-up (saa_b200.device_setup): mesh part, numbering, K6 assembly and the plan, all on the GPU."""
     import saa_b200  # noqa: F401
     from saa_b200 import device_setup
@@ -180,13 +184,14 @@ def setup_device(m, size, rank, local, partition="slabs"):
         pname = "METIS_PartMeshDual(ncommon=3) on the host mesh"
     else:
         kind = "blocks" if (partition == "blocks" and size > 1) else "slabs"
-        pl, info = device_setup.build_structured_rank(m, rank, size, device_index=local, partition=kind)
-        g = device_setup.block_grid(size) if kind == "blocks" else None
+        pl, info = device_setup.build_structured_rank(m, rank, size, device_index=local, partition=kind, grid=grid, keep_mesh=keep_mesh)
+        g = (grid or device_setup.block_grid(size)) if kind == "blocks" else None
         pname = ("none" if size == 1 else
                  f"{size} x-slabs of whole hexahedron layers (what a k-way cut of a 25:1:1 beam gives)" if kind == "slabs" else
                  f"{g[0]}x{g[1]}x{g[2]} blocks of hexahedra (up to {min(size - 1, 7)} neighbours per rank, nodes held by up to {size} ranks)")
     halo = info.get("halo")
-    return pl, dict(dt=float(info["dt"]), n_nodes=info["n_global_nodes"], n_elem=info["n_global_elem"], part=pname,
+    return pl, dict(mesh=({k: info[k] for k in ("cells_loc", "pts", "lame")} if keep_mesh else None),
+                    dt=float(info["dt"]), n_nodes=info["n_global_nodes"], n_elem=info["n_global_elem"], part=pname,
                     neighbours=(len(halo["neighbours"]) if halo else 0), shared_nodes=(len(halo["shared_pos"]) if halo else 0),
                     assembly="device (saa_assemble_stiffness_dev, closed-form element matrices)")
 
@@ -344,16 +349,16 @@ def parity_fixture(world, rank, local, transport, torch, dist):
 
 
 def parity_mid(world, rank, local, transport, torch, dist):
-    """Mid-size case (structured m = 8, METIS partition stored in the fixture: several boundary slices and shared-row units
+    """Mid-size case (3 x 1 x 1 beam, m = 14, METIS partition stored in the fixture: several boundary slices and shared-row units
     per rank, nodes held by >= 3 ranks): device set-up + fused peer step vs histories the CPU oracle produced from the
-    same device-assembled matrices (tests/golden/mid_m8_np{N}.npz, oracle/gen_golden_mid.py)."""
+    same device-assembled matrices (tests/golden/mid_np{N}.npz, oracle/gen_golden_mid.py)."""
     from saa_b200 import device_setup, mesh, multi, plan as splan
-    path = os.path.join(ROOT, "tests", "golden", f"mid_m8_np{world}.npz")
+    path = os.path.join(ROOT, "tests", "golden", f"mid_np{world}.npz")
     if not os.path.isfile(path):
         return None
     z = np.load(path)
     m = int(z["m"])
-    pts, cells, fac = mesh.structured_beam(m)
+    pts, cells, fac = mesh.structured_beam(m, length=int(z["length"]))
     pl, info = device_setup.build_mesh_rank(pts, cells, fac, z["epart"].astype(np.int64), rank, world, device_index=local)
     tr = multi.attach_transport(pl, transport)
     ok, done = True, 0
@@ -365,7 +370,7 @@ def parity_mid(world, rank, local, transport, torch, dist):
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     halo = info["halo"]
-    out = {"fixture": f"tests/golden/mid_m8_np{world}.npz (CPU oracle on the device-assembled matrices, METIS)", "transport": tr,
+    out = {"fixture": f"tests/golden/mid_np{world}.npz (CPU oracle on the device-assembled matrices, METIS)", "transport": tr,
            "n_dof": 3 * len(pts), "steps_compared": [int(x) for x in z["steps"]], "neighbours_rank0": len(halo["neighbours"]),
            "shared_nodes_rank0": len(halo["shared_pos"]), "bit_identical": bool(flag.item() >= 1.0)}
     pl.close()
@@ -594,7 +599,8 @@ def main():
         pl, info = setup_host(m, world, rank, local)
         info.update(neighbours=None, shared_nodes=None)
     else:
-        pl, info = setup_device(m, world, rank, local, args.partition)
+        grid = tuple(int(x) for x in args.blocks.lower().split("x")) if args.blocks else None
+        pl, info = setup_device(m, world, rank, local, args.partition, grid=grid, keep_mesh=(args.kernel == "matfree"))
         if world > 1 and args.balance and args.partition == "slabs":
             from saa_b200 import device_setup
             st0 = torch.cuda.ExternalStream(pl.stream, device=torch.device("cuda", local))
@@ -617,6 +623,33 @@ def main():
     dtv = info["dt"]
     mode = splan.MODE_SYNC if world > 1 else splan.MODE_LOCAL
     stream = torch.cuda.ExternalStream(pl.stream, device=torch.device("cuda", local))
+
+    matfree = None
+    if args.kernel == "matfree":
+        if world > 1 or args.setup != "device":
+            raise SystemExit("--kernel matfree: one GPU, device set-up (synchronised multi-partition steps stream the assembled matrix)")
+        # measured difference from the assembled (parity) path first: the same 1000 steps from rest with both kernels
+        msh = info["mesh"]
+        pl.set_matfree(msh["cells_loc"], msh["pts"], *msh["lame"])
+        k_cmp = 1000 if m <= 32 else 200
+        pl.step(k_cmp, splan.MODE_LOCAL)
+        pl.synchronize()
+        a = torch.empty(n_dof_local, dtype=torch.float64, device="cuda")
+        pl.get_state_dev(a.data_ptr(), None)
+        z = torch.zeros(n_dof_local, dtype=torch.float64, device="cuda")
+        pl.set_state_dev(z.data_ptr(), z.data_ptr(), 0.0)
+        mat_bytes = pl.matrix_bytes
+        pl.set_option(splan.OPT_MATFREE, 2)          # matrix-free from here on; the assembled matrix is released
+        pl.step(k_cmp, splan.MODE_LOCAL)
+        pl.synchronize()
+        b = torch.empty(n_dof_local, dtype=torch.float64, device="cuda")
+        pl.get_state_dev(b.data_ptr(), None)
+        matfree = {"rel_l2_vs_assembled": float(((a - b).norm() / a.norm()).item()), "after_steps": k_cmp,
+                   "bytes_streamed_besides_vectors": pl.matfree_bytes, "assembled_matrix_bytes": mat_bytes,
+                   "hbm_in_use_gb_after_release": (torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9}
+        del a, b, z, msh
+        info["mesh"] = None
+        torch.cuda.empty_cache()
 
     # ---- device-resident timing --------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
@@ -662,7 +695,7 @@ def main():
     # The scalar-CSR figure of SURVEY.md §8d (12 B per stored entry + 4 B per row pointer + 40 B per row) is given
     # beside it as csr_equivalent.
     nnz = pl.nnz
-    alg_bytes = max_over_ranks(float(pl.matrix_bytes + 5 * 8 * n_dof_local))
+    alg_bytes = max_over_ranks(float((pl.matfree_bytes if matfree else pl.matrix_bytes) + 5 * 8 * n_dof_local))
     csr_bytes = max_over_ranks(float(nnz * 12 + (n_dof_local + 1) * 4 + 5 * 8 * n_dof_local))
     step_s = ms * 1e-3 / steps
     peak, peak_src = measured_peak()
@@ -684,7 +717,7 @@ def main():
     torch.cuda.empty_cache()
 
     also = None
-    if not args.no_also and args.setup == "device" and m == M_DEFAULT:
+    if not args.no_also and args.setup == "device" and m == M_DEFAULT and not matfree:
         also = []
         # N > 1: config 3 is timed inside time_sync_avoiding (synchronised_every_step) unless that leg is off
         todo = [(24, 1, 2000), (65, 1, 500)] if world == 1 else ([(65, world, 500)] if args.sync_avoid in ("off", "", "none") else [])
@@ -739,13 +772,19 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "bytes_per_launch": alg_bytes, "bytes_formula": "76*blocks + 8*(slices+1) + 4*rows/32 + 40*rows (largest shard)",
+                         "bytes_per_launch": alg_bytes,
+                         "bytes_formula": ("16*elements + 4*incidence lanes + 24*nodes + 8*(slices+1) + 4*rows/32 + 40*rows" if matfree else
+                                           "76*blocks + 8*(slices+1) + 4*rows/32 + 40*rows (largest shard)"),
                          "csr_equivalent": {"bytes_per_launch": csr_bytes, "formula": "12*nnz + 4*(rows+1) + 40*rows",
                                             "achieved": csr_bytes / step_s / 1e9, "frac": csr_bytes / step_s / 1e9 / peak},
                          "blocks_per_node": blocks_per_node,
-                         "kernel": "saa_k_step (fused K.u + central-difference update + Dirichlet mask)"},
+                         "kernel": ("saa_k_step_matfree (K5: element-wise B^T D B u_e, node-owned, fused with the update) — fp64/L1-bound, "
+                                    "see profiles/" if matfree else "saa_k_step (fused K.u + central-difference update + Dirichlet mask)")},
             "clocks": clocks,
         }
+        if matfree:
+            line["matfree"] = matfree
+            line["config"]["kernel"] = "matfree (K5) — NOT the parity path; see line['matfree'].rel_l2_vs_assembled"
         if parity is not None:
             line["parity"] = parity
         if also is not None:

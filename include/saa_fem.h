@@ -162,10 +162,26 @@ int saa_plan_synchronize(saa_plan *plan);
  *   SAA_OPT_PEER_FUSED   1 (default): one fused launch per step with the peer transport; 0: boundary / interior /
  *                        shared-row kernels as three launches.
  *   SAA_OPT_PREFER_NCCL  1: use the NCCL transport (saa_plan_init_nccl) although peer memory is attached too.
+ *   SAA_OPT_MATFREE      1: un-synchronised steps evaluate f_int = sum_e B^T D B u_e element by element (kernel K5,
+ *                        saa_plan_set_matfree_dev) instead of streaming the assembled matrix — NOT bit-identical to the
+ *                        assembled path (different association), a throughput / low-memory mode.
+ *                        2: same, and the assembled matrix is released (single-partition plans; cannot be undone).
  */
 #define SAA_OPT_PEER_FUSED 1
 #define SAA_OPT_PREFER_NCCL 2
+#define SAA_OPT_MATFREE 3   /* 1: LOCAL / PREDICT steps (and SYNC steps of a single partition) use the matrix-free kernel K5 */
 int saa_plan_set_option(saa_plan *plan, int option, int value);
+
+/*
+ * Matrix-free internal force (north star: "matrix-free element-wise B^T.D.B.u_e gather/scatter ... made deterministic
+ * with ... CSR row ownership rather than atomics"): the element kernel of Tools/Mat_construction.py:79-119 applied to
+ * u_e instead of assembled (:122-150).  cells_dev: (n_elem, 4) int32 LOCAL node ids (positions in Local_nodal_list),
+ * coords_dev: (n_dof/3, 3) float64 coordinates of the local nodes, both in device memory (copied); lmd, mu: Lame
+ * constants (Data_prepare.py:47).  Enable with saa_plan_set_option(plan, SAA_OPT_MATFREE, 1).
+ */
+int saa_plan_set_matfree_dev(saa_plan *plan, int64_t n_elem, const int32_t *cells_dev, const double *coords_dev,
+                             double lmd, double mu);
+int64_t saa_plan_matfree_bytes(const saa_plan *plan); /* bytes K5 streams per step besides the vector streams     */
 /* the cudaStream_t the plan enqueues on (as void*), so that callers can record events on it */
 void *saa_plan_stream(saa_plan *plan);
 

@@ -5,6 +5,7 @@
 // Reference semantics restated here (paths under /root/reference): Tools/Dynamic_solver.py:9-34,
 // Tools/Distributed_tools.py:77-92, Data_prepare.py:223-240, Online_predictor.py:251-318.
 #include "saa_kernels.cuh"
+#include "saa_matfree.cuh"
 
 #include <dlfcn.h>
 
@@ -169,6 +170,13 @@ struct saa_plan {
     bool in_split_step = false;             // between saa_plan_step_begin_host and saa_plan_step_end_host
     int64_t state_epoch = 1, host_epoch = 0; // saa_step_host_ex: the device still holds the previous call's d0 iff equal
     double *d_force = nullptr;              // [2 * n_rows] scratch of the stand-alone force synchronisation
+    // matrix-free mode (K5, saa_plan_set_matfree_dev)
+    SaaMatFreeDev MF{};
+    int64_t *d_mf_slice_ptr = nullptr;
+    int32_t *d_mf_inc = nullptr, *d_mf_cells = nullptr;
+    double *d_mf_X = nullptr;
+    int64_t mf_elems = 0, mf_lanes = 0;
+    bool matfree = false;                   // SAA_OPT_MATFREE: local steps evaluate B^T D B u_e instead of streaming the matrix
 };
 
 struct saa_group {
@@ -527,7 +535,8 @@ extern "C" int saa_plan_destroy(saa_plan *p)
         void *ptrs[] = {p->d_slice_ptr, p->d_val, p->d_col, p->d_M, p->d_F, p->d_dir, p->d_iperm, p->d_buf[0], p->d_buf[1],
                         p->d_clk, p->d_stage, p->d_xbuf, p->d_send, p->d_dst_ptr, p->d_dst_pos, p->d_src_ptr, p->d_src_pos,
                         p->d_recv, p->d_done, p->d_own_ready, p->d_dst_nb, p->d_dst_pos_peer, p->d_peer_recv, p->d_peer_stride, p->d_peer_flag,
-                        p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force, p->d_hook};
+                        p->d_hist_rows, p->d_hist, p->d_pred_rows, p->d_force, p->d_hook,
+                        p->d_mf_slice_ptr, p->d_mf_inc, p->d_mf_cells, p->d_mf_X};
         for (void *q : ptrs)
             if (q) cudaFree(q);
         if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
@@ -789,7 +798,13 @@ static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, u
 
 static void launch_local_step(saa_plan *p, cudaStream_t st)
 {
-    launch_interior(p, st, 0, 0u, true);
+    if (p->matfree) {
+        saa_k_step_matfree<3><<<std::max(1u, nblk(p->n_slices, SAA_WARPS_PER_BLOCK)), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
+            p->D, p->MF, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1));
+        p->launches++;
+    } else {
+        launch_interior(p, st, 0, 0u, true);
+    }
     p->cur ^= 1;
 }
 
@@ -885,6 +900,7 @@ static int step_local(saa_plan *p, int64_t n_steps, int mode, int launch)
     const bool hooks = needs_hooks(p, mode);
     if (launch == SAA_LAUNCH_AUTO) launch = (n_steps >= 2 ? SAA_LAUNCH_GRAPH : SAA_LAUNCH_PER_STEP);   // graphs exist since finalize
     if (hooks && launch == SAA_LAUNCH_PERSISTENT) return fail("history / prediction hooks are not available in the persistent loop");
+    if (p->matfree && launch == SAA_LAUNCH_PERSISTENT) return fail("the matrix-free kernel has no persistent form");
     if (check_prediction(p, mode, n_steps)) return -1;
     if (hooks && launch == SAA_LAUNCH_GRAPH && n_steps >= 2) return step_hook_graph(p, n_steps, mode);
     if (launch == SAA_LAUNCH_PERSISTENT) {
@@ -1050,6 +1066,21 @@ extern "C" int saa_plan_set_option(saa_plan *p, int option, int value)
             if (p->graph_peer[i]) { cudaGraphExecDestroy(p->graph_peer[i]); p->graph_peer[i] = nullptr; }
         p->hook_epoch++;                                 // graphs of hooked synchronised steps hold the old form too
         return p->peer ? prepare_graphs(p, true) : 0;
+    }
+    if (option == SAA_OPT_MATFREE) {
+        if (value && !p->d_mf_inc) return fail("saa_plan_set_option: SAA_OPT_MATFREE needs saa_plan_set_matfree_dev first");
+        if (!value && !p->d_val) return fail("saa_plan_set_option: the assembled matrix of this plan was released (SAA_OPT_MATFREE = 2)");
+        if (value == 2 && p->d_val) {                    // release the assembled matrix: the plan is matrix-free for good
+            if (p->size > 1) return fail("saa_plan_set_option: SAA_OPT_MATFREE = 2 is for single-partition plans (synchronised steps stream the matrix)");
+            cudaFree(p->d_val); cudaFree(p->d_col);
+            p->d_val = nullptr; p->d_col = nullptr; p->D.val = nullptr; p->D.col = nullptr;
+        }
+        if ((value != 0) == p->matfree) return 0;
+        p->matfree = value != 0;
+        for (int i = 0; i < 2; ++i)
+            if (p->graph_exec[i]) { cudaGraphExecDestroy(p->graph_exec[i]); p->graph_exec[i] = nullptr; }
+        p->hook_epoch++;
+        return prepare_graphs(p, false);
     }
     if (option == SAA_OPT_PREFER_NCCL) {
         if (value && !p->comm) return fail("saa_plan_set_option: SAA_OPT_PREFER_NCCL needs saa_plan_init_nccl first");
@@ -1371,3 +1402,42 @@ extern "C" int saa_plan_init_nccl(saa_plan *p, const void *id128)
 }
 
 #include "saa_device_setup.cuh"
+
+// ---- matrix-free mode (K5) ------------------------------------------------------------------------------------
+extern "C" int saa_plan_set_matfree_dev(saa_plan *p, int64_t n_elem, const int32_t *cells_dev, const double *coords_dev, double lmd, double mu)
+{
+    NEED_FINAL(p, "saa_plan_set_matfree_dev");
+    if (n_elem <= 0 || !cells_dev || !coords_dev) return fail("saa_plan_set_matfree_dev: null or empty argument");
+    if (p->d_mf_inc) return fail("saa_plan_set_matfree_dev: already set");
+    CK(cudaSetDevice(p->device));
+    const int64_t nn_ext = p->n_dof / 3, nn_int = p->n_rows / 3;
+    CK(cudaMalloc((void **)&p->d_mf_cells, 4 * n_elem * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&p->d_mf_X, 3 * nn_int * sizeof(double)));
+    CK(cudaMemset(p->d_mf_X, 0, 3 * nn_int * sizeof(double)));
+    saa_k_mf_cells_to_internal<<<nblk(4 * n_elem, 256), 256>>>(4 * n_elem, cells_dev, p->d_iperm, p->d_mf_cells);
+    saa_k_mf_coords_to_internal<<<nblk(nn_ext, 256), 256>>>(nn_ext, coords_dev, p->d_iperm, p->d_mf_X);
+    CK(cudaGetLastError());
+    DevBuf inc_ptr, inc_slot, width;
+    if (build_incidence(nn_int, n_elem, p->d_mf_cells, inc_ptr, inc_slot)) return -1;     // ascending element order per node
+    if (width.alloc((p->n_slices + 1) * sizeof(int64_t))) return -1;
+    CK(cudaMalloc((void **)&p->d_mf_slice_ptr, (p->n_slices + 1) * sizeof(int64_t)));
+    saa_k_mf_slice_width<<<nblk(p->n_slices + 1, 256), 256>>>(p->n_slices, inc_ptr.as<int64_t>(), width.as<int64_t>());
+    thrust::exclusive_scan(thrust::device, width.as<int64_t>(), width.as<int64_t>() + p->n_slices + 1, p->d_mf_slice_ptr);
+    CK(cudaMemcpy(&p->mf_lanes, p->d_mf_slice_ptr + p->n_slices, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMalloc((void **)&p->d_mf_inc, std::max<int64_t>(p->mf_lanes, 1) * sizeof(int32_t)));
+    saa_k_mf_fill<<<nblk(nn_int, 256), 256>>>(nn_int, inc_ptr.as<int64_t>(), inc_slot.as<int32_t>(), p->d_mf_slice_ptr, p->d_mf_inc);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    p->mf_elems = n_elem;
+    p->MF.slice_ptr = p->d_mf_slice_ptr; p->MF.inc = p->d_mf_inc; p->MF.cells = (const int4 *)p->d_mf_cells; p->MF.X = p->d_mf_X;
+    p->MF.lmd = lmd; p->MF.mu = mu;
+    return 0;
+}
+
+// bytes the matrix-free kernel streams per time step besides the five vector streams: connectivity, incidence
+// (incl. slice padding), coordinates, slice offsets, Dirichlet mask words
+extern "C" int64_t saa_plan_matfree_bytes(const saa_plan *p)
+{
+    if (!p || !p->d_mf_inc) return -1;
+    return 16 * p->mf_elems + 4 * p->mf_lanes + 24 * (p->n_rows / 3) + (p->n_slices + 1) * 8 + (p->n_rows / 32) * 4;
+}

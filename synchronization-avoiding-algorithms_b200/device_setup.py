@@ -283,7 +283,7 @@ def gather_node_lists(local_nodes, size):
 
 # ---- one rank of a structured cantilever, end to end --------------------------------------------------------------
 def rank_local(cells_global, points_of, clamped_of, rank, size, device_index=0, E=E_DEFAULT, nu=NU_DEFAULT, rho=RHO_DEFAULT,
-               fz=FZ_DEFAULT, gamma=GAMMA_DEFAULT, n_global_nodes=0, n_global_elem=0, reorder=None):
+               fz=FZ_DEFAULT, gamma=GAMMA_DEFAULT, n_global_nodes=0, n_global_elem=0, reorder=None, keep_mesh=False):
     """Phase 1 (no communication) for ANY tetrahedral mesh: `cells_global` (nE_loc,4) int64 device tensor with the
     global node ids of this rank's elements in ascending element order (Local_ele_list order); points_of(ids) ->
     (n,3) float64 device coordinates of the given global node ids; clamped_of(ids) -> bool device mask of clamped
@@ -297,7 +297,8 @@ def rank_local(cells_global, points_of, clamped_of, rank, size, device_index=0, 
     dt_loc = gamma * min_edge_meshsize(cells_loc, pts) / np.sqrt(E / rho / (1 - nu ** 2))     # Data_prepare.py:147
     clamped = torch.nonzero(clamped_of(local_nodes)).reshape(-1).cpu().numpy()                 # (:127-144) ascending local position
     node_order = morton_node_order(pts) if reorder == "morton" else None
-    return dict(node_order=node_order, rank=rank, size=size, device_index=device_index, local_nodes=local_nodes, n_nodes=local_nodes.numel(),
+    return dict(cells_loc=cells_loc, pts=pts, lame=(lmd, mu), keep_mesh=keep_mesh,
+                node_order=node_order, rank=rank, size=size, device_index=device_index, local_nodes=local_nodes, n_nodes=local_nodes.numel(),
                 n_elem=cells_loc.shape[0], K=K, m_node=m_node, F=F, dt_loc=float(dt_loc),
                 dirichlet=maps.node_to_dof(3, [0, 1, 2], clamped), n_global_nodes=n_global_nodes, n_global_elem=n_global_elem)
 
@@ -384,6 +385,10 @@ def structured_rank_plan(loc, halo, recv, dt, alpha=DAMP_DEFAULT, keep_csr=False
                               rank=rank, size=size, node_order=loc.get("node_order"))
     info = dict(n_nodes=loc["n_nodes"], n_elem=loc["n_elem"], nnz=K.nnz, dt=dt, local_nodes=loc["local_nodes"], halo=halo,
                 n_global_nodes=loc["n_global_nodes"], n_global_elem=loc["n_global_elem"])
+    if loc.get("keep_mesh"):                       # local connectivity / coordinates for the matrix-free kernel (StepPlan.set_matfree)
+        info.update(cells_loc=loc["cells_loc"], pts=loc["pts"], lame=loc["lame"])
+    else:
+        loc.pop("cells_loc", None); loc.pop("pts", None)
     if keep_csr:
         info.update(K=K, F=loc["F"], lM=lM, dirichlet=loc["dirichlet"])
     else:

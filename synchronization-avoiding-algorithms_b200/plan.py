@@ -24,7 +24,7 @@ _lib = None
 MODE_LOCAL, MODE_SYNC, MODE_PREDICT = 0, 1, 2
 LAUNCH_AUTO, LAUNCH_PER_STEP, LAUNCH_GRAPH, LAUNCH_PERSISTENT = 0, 1, 2, 3
 HOST_DN_IS_PREVIOUS_D0 = 1
-OPT_PEER_FUSED, OPT_PREFER_NCCL = 1, 2
+OPT_PEER_FUSED, OPT_PREFER_NCCL, OPT_MATFREE = 1, 2, 3
 
 # every symbol include/saa_fem.h declares: name -> (restype, argtypes)
 _vp, _i64, _i32, _f64, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_int
@@ -55,6 +55,8 @@ ABI = {
     "saa_plan_step": (_int, [_vp, _i64, _int, _int]),
     "saa_plan_synchronize": (_int, [_vp]),
     "saa_plan_set_option": (_int, [_vp, _int, _int]),
+    "saa_plan_set_matfree_dev": (_int, [_vp, _i64, _vp, _vp, _f64, _f64]),
+    "saa_plan_matfree_bytes": (_i64, [_vp]),
     "saa_plan_stream": (_vp, [_vp]),
     "saa_step_host": (_int, [_vp, _vp, _vp, _f64, _int, _vp]),
     "saa_step_host_ex": (_int, [_vp, _vp, _vp, _f64, _int, _vp, _int]),
@@ -273,6 +275,26 @@ class StepPlan:
 
     def set_option(self, option, value):
         _check(lib().saa_plan_set_option(self.h, int(option), int(value)), "saa_plan_set_option")
+
+    def set_matfree(self, cells_local, coords_local, lmd, mu):
+        """Hand the element connectivity (nE,4; local node ids) and the local node coordinates (n,3) to the plan for the
+        matrix-free kernel K5 (torch CUDA tensors, or host arrays which are uploaded through torch); enable it with
+        set_option(OPT_MATFREE, 1)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        c = cells_local if isinstance(cells_local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cells_local, dtype=np.int32))
+        x = coords_local if isinstance(coords_local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(coords_local, dtype=np.float64))
+        c = c.to(device=dev, dtype=torch.int32).contiguous()
+        x = x.to(device=dev, dtype=torch.float64).contiguous()
+        if c.ndim != 2 or c.shape[1] != 4 or x.shape != (self.n_dof // 3, 3):
+            raise SaaError("set_matfree: cells must be (nE,4) and coords (n_dof/3, 3)")
+        torch.cuda.synchronize(dev)
+        _check(lib().saa_plan_set_matfree_dev(self.h, c.shape[0], c.data_ptr(), x.data_ptr(), float(lmd), float(mu)),
+               "saa_plan_set_matfree_dev")
+
+    @property
+    def matfree_bytes(self):
+        return int(lib().saa_plan_matfree_bytes(self.h))
 
     def step_host(self, d0, dn, tn, mode=MODE_LOCAL, out=None):
         """One parallel_explicit_solver_dis_pre evaluation with host buffers -> d1 (n_dof,).

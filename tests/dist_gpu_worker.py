@@ -4,7 +4,7 @@ peer-memory (NVLink) or NCCL transport must reproduce golden histories bit for b
     dist_gpu_worker.py <peer|nccl> <fixture>
 
 fixture = beam_coarse_P{N}: histories of the unmodified reference (110 nodes, one boundary slice per rank);
-          mid_m8_np{N}:     CPU-oracle histories of the 48 843-DOF METIS case (oracle/gen_golden_mid.py): several boundary
+          mid_np{N}:     CPU-oracle histories of the 29 025-DOF METIS case (oracle/gen_golden_mid.py): several boundary
                             slices and shared-row units per rank, nodes held by >= 3 ranks, device set-up.
 When the box has fewer GPUs than ranks the ranks share the GPUs (gloo process group, peer transport only: the
 receive areas are mapped through CUDA IPC all the same, the kernels of the ranks time-slice on the device).
@@ -39,7 +39,7 @@ rank, size = dist.get_rank(), dist.get_world_size()
 if golden.startswith("mid_"):
     z = np.load(os.path.join(GOLDEN, golden + ".npz"))
     assert int(z["size"]) == size
-    pts, cells, fac = mesh.structured_beam(int(z["m"]))
+    pts, cells, fac = mesh.structured_beam(int(z["m"]), length=int(z["length"]))
     pl, info = device_setup.build_mesh_rank(pts, cells, fac, z["epart"].astype(np.int64), rank, size, device_index=local)
     steps, hist = [int(x) for x in z["steps"]], (lambda s: z[f"hist_{s}_r{rank}"])
 else:

@@ -258,16 +258,16 @@ def _run_workers(transport, name, n, timeout=600):
 def _have_mid(n):
     import os
     from util import GOLDEN
-    return os.path.isfile(os.path.join(GOLDEN, f"mid_m8_np{n}.npz"))
+    return os.path.isfile(os.path.join(GOLDEN, f"mid_np{n}.npz"))
 
 
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("name,n", [("beam_coarse_P2", 2), ("beam_coarse_P4", 4), ("beam_coarse_P8", 8),
-                                    ("mid_m8_np2", 2), ("mid_m8_np4", 4), ("mid_m8_np8", 8)])
+                                    ("mid_np2", 2), ("mid_np4", 4), ("mid_np8", 8)])
 def test_one_process_per_gpu_transports(transport, name, n):
     """N GPUs of one box, one process each: NVLink peer-memory stores (fused single-launch step and its three-kernel
     form) / NCCL send-recv reproduce the reference's syn_cpus histories bit for bit (skipped when the box has fewer
-    GPUs).  mid_*: 48 843 DOF in METIS partitions — several boundary slices and shared-row units per rank."""
+    GPUs).  mid_*: 29 025 DOF in METIS partitions — several boundary slices and shared-row units per rank."""
     if _ngpu() < n:
         pytest.skip(f"needs {n} GPUs")
     if name.startswith("mid_") and not _have_mid(n):
@@ -283,7 +283,7 @@ def test_fused_peer_step_two_processes_sharing_this_gpu():
 
 
 def test_mid_fixture_is_reproducible():
-    """tests/golden/mid_m8_np*.npz were produced on another B200 box by oracle/gen_golden_mid.py (device assembly -> CPU
+    """tests/golden/mid_np*.npz were produced on another B200 box by oracle/gen_golden_mid.py (device assembly -> CPU
     oracle).  Regenerating them here must give the same bits (deterministic device assembly, same METIS partition), and
     the CUDA group run on those matrices must reproduce them."""
     import os
@@ -295,13 +295,13 @@ def test_mid_fixture_is_reproducible():
     import gen_golden_mid
     from saa_b200 import device_setup
     for P in (4, 8):
-        z = np.load(os.path.join(GOLDEN, f"mid_m8_np{P}.npz"))
+        z = np.load(os.path.join(GOLDEN, f"mid_np{P}.npz"))
         g = gen_golden_mid.generate(P)
         assert np.array_equal(g["epart"], z["epart"])
         for s in (int(x) for x in z["steps"]):
             for q in range(P):
                 assert bits_equal(g[f"hist_{s}_r{q}"], z[f"hist_{s}_r{q}"]), (P, s, q)
-        pts, cells, fac = mesh.structured_beam(int(z["m"]))
+        pts, cells, fac = mesh.structured_beam(int(z["m"]), length=int(z["length"]))
         plans, infos = device_setup.build_mesh_in_process(pts, cells, fac, z["epart"].astype(np.int64), P)
         grp = splan.PlanGroup(plans)
         done = 0
