@@ -7,9 +7,11 @@ set-up :66-235, loop :251-318, output :321-324) with the time loop resident on t
         examples/online_predictor_driver.py --mesh beam.vtk --steps 400 --n-past 4 --n-future 3 --filter-size 5 [--model-dir DIR]
 
 Every rank: warm-up of n_past*filter_size synchronised steps, then refill blocks in which the rank's LSTM
-encoder-decoder (weights from DIR/Rank-<r>/model.pth as written by the reference's Model_training.py, or seeded
-random weights when no directory is given) predicts its shared-DOF displacements on the device and the FE steps run
-without any exchange.  --resync K adds a true exchange every K steps.  Ranks may share a GPU: the warm-up
+encoder-decoder predicts its shared-DOF displacements on the device and the FE steps run without any exchange.
+--model-dir DIR names the directory the reference's Model_training.py writes into (`Distributed_save`): the weights are
+read from DIR/Rank-<r>/nB-<nB>-nH-<hidden>-Lr-<lr>-filter=<filter>/model.pth (Online_predictor.py:139-141) and the scaling
+constants are recomputed the way the reference does (:130-136) from Results/sol_on_shared/rank=<r>-shared_dof.hdf5 under
+--out (training windows of the first --cut-off fraction, joint extrema).  Without --model-dir: seeded random weights.  --resync K adds a true exchange every K steps.  Ranks may share a GPU: the warm-up
 exchange then travels through host memory with the process group (gloo / MPI).
 Writes Results/Dynamics/Modeled_Local-rank-<r>.hdf5 (dataset 'Displacement', (3n, n_saved)).
 """
@@ -38,6 +40,9 @@ ap.add_argument("--n-future", type=int, default=20)
 ap.add_argument("--filter-size", type=int, default=150)
 ap.add_argument("--hidden", type=int, default=50)
 ap.add_argument("--model-dir", default="")
+ap.add_argument("--nB", type=int, default=10)
+ap.add_argument("--learning-rate", type=float, default=5e-4)
+ap.add_argument("--cut-off", type=float, default=0.5)
 ap.add_argument("--resync", type=int, default=0)
 args = ap.parse_args()
 
@@ -49,7 +54,10 @@ os.makedirs(out_dir, exist_ok=True)
 # mesh + partition (every rank reads the mesh; the partition call is the driver's, Online_predictor.py:94-114)
 Mesh = meshio.read(args.mesh)
 Cells, Facets, Points = Mesh.cells_dict['tetra'], Mesh.cells_dict['triangle'], Mesh.points
-bounds = np.linspace(0, len(Cells), size + 1).astype(int)
+# element chunks handed to ParMETIS: the reference's elmdist (Online_predictor.py:83-86)
+nEach = len(Cells) // size
+nLeft = len(Cells) - nEach * size
+bounds = np.append((nEach + 1) * np.arange(nLeft + 1), ((nEach + 1) * nLeft) + nEach * np.arange(1, size - nLeft + 1)).astype(np.int64)
 mine = np.asarray(Cells[bounds[rank]:bounds[rank + 1]], dtype=np.int64)
 _, epart = part_mesh_kway(size, 4 * np.arange(len(mine) + 1, dtype=np.int64), mine.reshape(-1))
 recvbuf = np.empty(len(Cells), dtype='int') if rank == 0 else None
@@ -77,9 +85,13 @@ class HostExchangeStepper:
 
 # surrogate (Online_predictor.py:139-141) and scaling constants (:130-136)
 if args.model_dir:
-    model = call_model("cuda", args.filter_size, input_size, args.hidden, os.path.join(args.model_dir, f"Rank-{rank}", "model.pth"))
-    sc = np.loadtxt(os.path.join(args.model_dir, f"Rank-{rank}", "scale.csv"), delimiter=",")
-    scale_max, scale_min = float(sc[0]), float(sc[1])
+    data_path = os.path.join(args.out, "Results", "sol_on_shared", f"rank={rank}-shared_dof.hdf5")
+    X, Y = Dis_data_filtered_subset_coronary("cpu", input_size, args.filter_size, args.n_past, args.n_future, data_path, args.cut_off)
+    _, _, scale_max, scale_min = Scale_to_zero_one(X, Y)                              # :130-136
+    scale_max, scale_min = float(scale_max), float(scale_min)
+    model_path = os.path.join(args.model_dir, f"Rank-{rank}", f"nB-{args.nB}-nH-{args.hidden}-Lr-{args.learning_rate}-filter={args.filter_size}",
+                              "model.pth")                                            # :139-140
+    model = call_model("cuda", args.filter_size, input_size, args.hidden, model_path)
 else:
     torch.manual_seed(100 + rank)
     model = LSTM_encoder_decoder(max(input_size, 1), args.hidden, 2, True, 0.0, 0.0)
