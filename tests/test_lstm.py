@@ -352,3 +352,62 @@ def test_chunked_sync_avoiding_run_equals_single_run(resync):
         span = smax - smin
         for q in range(2):
             assert np.abs(outs[1][1][q] - z[f"d_sol_r{q}"][T - cap:]).max() <= 5e-5 * span
+
+
+@pytest.mark.gpu
+def test_pipeline_with_surrogates_trained_by_the_unmodified_reference_script(tmp_path):
+    """The reference's four-script pipeline (README.md:33-38) end to end on the GPU with the REFERENCE'S OWN training:
+      1. Data_prepare-shaped run, 2 ranks, 30 000 synchronised steps of beam_coarse (examples/data_prepare_driver.py);
+      2. shared-DOF extraction (the row selection of Shared_extraction.py:27-40);
+      3. surrogates = tests/golden/model_training_ref_rank{0,1}.pth — written by the reference's UNMODIFIED
+         Model_training.py (3450 epochs, its own hyper-parameters) run through run_driver.py in the authoring container on
+         this very history (profiles/r2/model_training_unchanged_2ranks_cpu.log), placed in the directory layout that script
+         uses (Distributed_save/Rank-r/nB-10-nH-50-Lr-0.0005-filter=150/model.pth);
+      4. Online_predictor-shaped run (examples/online_predictor_driver.py --model-dir): 3 000 synchronised warm-up steps,
+         then one refill block of 3 000 un-synchronised steps driven by the surrogates, scaling constants recomputed from
+         the extracted history as Online_predictor.py:130-136 does.
+    The warm-up must equal the synchronised run bit for bit; the modelled block is compared with it as a relative L2 error."""
+    import subprocess
+    import shutil
+    import saa_b200  # noqa: F401
+    from saa_b200 import mesh
+    for q in range(2):
+        if not os.path.isfile(os.path.join(GOLDEN, f"model_training_ref_rank{q}.pth")):
+            pytest.skip("reference-trained surrogate fixtures not present")
+    g = load_golden("beam_coarse_P2")
+    vtk = str(tmp_path / "m.vtk")
+    mesh.write_vtk(vtk, g["points"], g["cells"], g["facets"])
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([PKG, os.path.join(PKG, "compat")])
+    T_sync, n_p, n_f, n_s = 30000, 20, 20, 150
+    port = 29800 + os.getpid() % 150
+    tr = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port"]
+    r = subprocess.run(tr + [str(port), os.path.join(ROOT, "examples", "data_prepare_driver.py"), "--mesh", vtk, "--steps", str(T_sync),
+                             "--out", str(tmp_path)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    os.makedirs(tmp_path / "Results" / "sol_on_shared", exist_ok=True)
+    sync = []
+    for q in range(2):
+        D = np.load(str(tmp_path / "Results" / "Dynamics" / f"Local-rank-{q}.hdf5.npz"))["Displacement"]
+        sync.append(D)
+        sh = np.loadtxt(str(tmp_path / "Results" / "Shared_Data" / f"Rank={q}_shared.csv"), dtype=np.int64, ndmin=1)
+        assert np.array_equal(sh, g["ranks"][q]["shared"])                      # same partition as the one the surrogates were trained on
+        np.savez_compressed(str(tmp_path / "Results" / "sol_on_shared" / f"rank={q}-shared_dof.hdf5.npz"),
+                            Displacement=D[g["ranks"][q]["loc_dof_shared"], :])   # Shared_extraction.py:27-40
+        d = tmp_path / "Distributed_save" / f"Rank-{q}" / "nB-10-nH-50-Lr-0.0005-filter=150"
+        os.makedirs(d, exist_ok=True)
+        shutil.copy(os.path.join(GOLDEN, f"model_training_ref_rank{q}.pth"), str(d / "model.pth"))
+    T = n_p * n_s + n_f * n_s
+    r = subprocess.run(tr + [str(port + 1), os.path.join(ROOT, "examples", "online_predictor_driver.py"), "--mesh", vtk, "--steps", str(T),
+                             "--out", str(tmp_path), "--model-dir", str(tmp_path / "Distributed_save")], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    for q in range(2):
+        got = np.load(str(tmp_path / "Results" / "Dynamics" / f"Modeled_Local-rank-{q}.hdf5.npz"))["Displacement"]
+        ref = sync[q][:, :T]
+        assert bits_equal(got[:, :n_p * n_s], ref[:, :n_p * n_s])               # synchronised warm-up (Online_predictor.py:251-270)
+        err_end = np.linalg.norm(got[:, -1] - ref[:, -1]) / np.linalg.norm(ref[:, -1])
+        err_all = np.linalg.norm(got[:, n_p * n_s:] - ref[:, n_p * n_s:]) / np.linalg.norm(ref[:, n_p * n_s:])
+        print(f"rank {q}: modelled vs synchronised displacement, refill block of {n_f * n_s} steps: rel-L2 {err_all:.3e} over the block, "
+              f"{err_end:.3e} at its end")
+        assert err_all <= 0.05 and err_end <= 0.1
