@@ -91,7 +91,7 @@ struct SaaHaloDev {
     unsigned int *done_ctr;                 // blocks of the pack kernel that have finished (last one raises the flags)
     unsigned long long *own_ready;          // fused step: number of steps whose own boundary forces are complete
     unsigned int *err;                      // set when a bounded wait expired (a peer never delivered)
-    unsigned int *tail_ticket;              // fused step: blocks that have finished their slices (the last ones take the shared rows)
+    unsigned int *tail_ticket;              // fused step: [0..1], [8..9] two sets of (finished blocks, claimed shared-row units); [16] fused-launch number
     int dbg;                                // -DSAA_DEBUG_PEER builds only (timing experiments): 1 no waits, 2 local stores,
                                             // 4 skip the shared rows, 8 treat boundary slices as interior
 };
@@ -416,11 +416,11 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
 //     neighbours' receive areas; the warp that completes the last boundary slice raises the neighbours' arrival
 //     flags (system scope) and the local "own forces ready" flag;
 //   * the bulk of the grid streams the interior slices, overlapping the NVLink traffic;
-//   * every block takes a ticket when it has FINISHED its slices; the last `tail_workers` finishers wait for the
-//     arrival flags, then do the rank-ordered sum and the update of the shared rows (units of 256 rows, strided
-//     over the workers).  Correctness does not depend on the order in which blocks are dispatched: waiting blocks
-//     have no slices left, and at most tail_workers (< resident capacity of the GPU) of them exist, so every
-//     block that has not run yet always finds a free slot.
+//   * every block that has FINISHED its slices looks at the arrival flags; once the messages are there, finishing
+//     blocks claim the shared rows in units of 256 (rank-ordered sum + update) until none is left; the last
+//     `tail_workers` finishers wait for the flags if they must.  Correctness does not depend on the order in which
+//     blocks are dispatched: waiting blocks have no slices left, and at most tail_workers (< resident capacity of
+//     the GPU) of them exist, so every block that has not run yet always finds a free slot.
 // Same arithmetic, same order as the three-kernel sequence — one launch gap and no pipeline drain per step.
 //   count_sync: 1 on synchronised steps (advances the exchange counter), 0 on local ones.
 #ifdef SAA_DEBUG_PEER          // timing experiments only (profiling builds): results are WRONG when H.dbg != 0
@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
 {
     const unsigned long long step = clk_in->sync_step;
     const double tn = clk_in->tn;
+    const unsigned int seq = (tail_workers != 0u) ? *((volatile const unsigned int *)(H.tail_ticket + 16)) : 0u;
     if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         clk_out->tn = __dadd_rn(tn, P.dt);
         clk_out->sync_step = step + count_sync;
@@ -474,32 +475,55 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
         }
     }
     if (tail_workers == 0u) return;                   // local step / interior phase: no shared rows in this launch
-    // ---- shared rows: the last `tail_workers` blocks to finish their slices
-    __shared__ unsigned int s_ticket;
+    // ---- shared rows, in units of 256.  A block that has finished its slices takes a ticket and looks at the arrival
+    // flags: if every message (and the own boundary forces) is already there it claims units until none is left, so the
+    // shared rows are normally done in the shadow of the interior stream; otherwise it leaves — unless it is one of the
+    // LAST `tail_workers` finishers, which wait (bounded) and drain whatever is left.  The counters exist twice; a
+    // launch uses the set selected by the parity of the fused-launch sequence number (device memory, read before the
+    // slices), and the very last finisher clears the other set and advances the number for the next fused launch.
+    __shared__ unsigned int s_go, s_unit;
+    unsigned int *cnt = H.tail_ticket + 8u * (seq & 1u);   // [0] finished blocks, [1] claimed units
+    const unsigned int n_units = (unsigned int)((H.sh_rows + 255) >> 8);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(H.tail_ticket, 1u);
-        if (t == gridDim.x - 1u) *H.tail_ticket = 0u; // last ticket of this launch: re-arm (the next launch is stream-ordered)
-        s_ticket = t;
+        const unsigned int t = atomicAdd(cnt, 1u);
+        if (t == gridDim.x - 1u) {                    // every block has read `seq` by now
+            unsigned int *nxt = H.tail_ticket + 8u * ((seq & 1u) ^ 1u);
+            nxt[0] = 0u; nxt[1] = 0u;
+            __threadfence();
+            *((volatile unsigned int *)(H.tail_ticket + 16)) = seq + 1u;
+        }
+        const unsigned int claimed = *((volatile unsigned int *)(cnt + 1));
+        bool ready = ld_acquire_gpu_u64(H.own_ready) >= step + 1ull;
+        for (int k = 0; k < H.n_nb; ++k) ready = ready && (ld_acquire_sys_u64(H.flags + k) >= step + 1ull);
+        const bool last = t >= gridDim.x - tail_workers;
+        s_go = (claimed >= n_units || SAA_DBG(H, 4)) ? 0u : (ready || SAA_DBG(H, 1)) ? 1u : last ? 2u : 0u;
     }
     __syncthreads();
-    const unsigned int first = gridDim.x - tail_workers;
-    if (s_ticket < first || SAA_DBG(H, 4)) return;
-    if (!SAA_DBG(H, 1)) {
+    if (s_go == 0u) return;
+    if (s_go == 2u) {
         if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
         if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
+        __syncthreads();
     }
-    __syncthreads();
     const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
     const double ramp = saa_ramp(tn);
-    for (int64_t row = (int64_t)(s_ticket - first) * blockDim.x + threadIdx.x; row < H.sh_rows; row += (int64_t)tail_workers * blockDim.x) {
-        double Fi = 0.0;
-        for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
-            const int32_t q = H.src_pos[k];
-            const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
-            Fi = __dadd_rn(Fi, v);
+    for (;;) {
+        if (threadIdx.x == 0) s_unit = atomicAdd(cnt + 1, 1u);
+        __syncthreads();
+        const unsigned int u = s_unit;
+        if (u >= n_units) break;
+        const int64_t row = (int64_t)u * 256 + threadIdx.x;
+        if (row < H.sh_rows) {
+            double Fi = 0.0;
+            for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+                const int32_t q = H.src_pos[k];
+                const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
+                Fi = __dadd_rn(Fi, v);
+            }
+            saa_finish_row(P, row, Fi, d0, dn_d1, ramp);
         }
-        saa_finish_row(P, row, Fi, d0, dn_d1, ramp);
+        __syncthreads();                              // s_unit is rewritten in the next round
     }
 }
 
