@@ -695,7 +695,7 @@ def main():
     # The scalar-CSR figure of SURVEY.md §8d (12 B per stored entry + 4 B per row pointer + 40 B per row) is given
     # beside it as csr_equivalent.
     nnz = pl.nnz
-    alg_bytes = max_over_ranks(float((pl.matfree_bytes if matfree else pl.matrix_bytes) + 5 * 8 * n_dof_local))
+    alg_bytes = max_over_ranks(float((pl.matfree_bytes if matfree else pl.matrix_bytes) + pl.vector_bytes))
     csr_bytes = max_over_ranks(float(nnz * 12 + (n_dof_local + 1) * 4 + 5 * 8 * n_dof_local))
     step_s = ms * 1e-3 / steps
     peak, peak_src = measured_peak()
@@ -730,7 +730,7 @@ def main():
                 md2 = splan.MODE_SYNC if w2 > 1 else splan.MODE_LOCAL
                 r2, _ = time_repeats(pl2, torch, st2, k2, md2, launch, barrier, max_over_ranks, 5, 200.0, 10)
                 ms2 = float(np.median(r2))
-                b2 = max_over_ranks(float(pl2.matrix_bytes + 40 * pl2.n_dof))
+                b2 = max_over_ranks(float(pl2.matrix_bytes + pl2.vector_bytes))
                 also.append({"workload": workload_name(m2, 3 * info2["n_nodes"], info2["n_elem"]), "n_gpus": w2, "steps": k2, "repeats": len(r2),
                              "value": 3 * info2["n_nodes"] * k2 / (ms2 * 1e-3), "ms_per_step": ms2 / k2,
                              "ms_per_step_min": min(r2) / k2, "ms_per_step_max": max(r2) / k2,
@@ -773,8 +773,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "bytes_per_launch": alg_bytes,
-                         "bytes_formula": ("16*elements + 4*incidence lanes + 24*nodes + 8*(slices+1) + 4*rows/32 + 40*rows" if matfree else
-                                           "76*blocks + 8*(slices+1) + 4*rows/32 + 40*rows (largest shard)"),
+                         "bytes_formula": ("16*elements + 4*incidence lanes + 24*nodes + 8*(slices+1) + 4*rows/32 + 32*rows + 8*nodes" if matfree else
+                                           "76*blocks + 8*(slices+1) + 4*rows/32 + 32*rows + 8*nodes (largest shard; lumped mass streamed per node)"),
                          "csr_equivalent": {"bytes_per_launch": csr_bytes, "formula": "12*nnz + 4*(rows+1) + 40*rows",
                                             "achieved": csr_bytes / step_s / 1e9, "frac": csr_bytes / step_s / 1e9 / peak},
                          "blocks_per_node": blocks_per_node,

@@ -142,6 +142,7 @@ int64_t saa_plan_nnz(const saa_plan *plan);           /* stored entries of Local
 int64_t saa_plan_padded_entries(const saa_plan *plan);/* entries streamed per step incl. slice padding    */
 int64_t saa_plan_kernel_launches(const saa_plan *plan);/* kernels launched by this plan so far            */
 int64_t saa_plan_matrix_bytes(const saa_plan *plan);  /* bytes of matrix storage streamed per step        */
+int64_t saa_plan_vector_bytes(const saa_plan *plan);  /* bytes of the vector streams of one step (d0, dn, d1, F, M; padded rows) */
 
 /* State = (d0, dn, tn) of Time_integration_displacement (commons.py:47-52), local DOF order. */
 int saa_plan_set_state(saa_plan *plan, const double *d0_host, const double *dn_host, double tn);

@@ -1,9 +1,9 @@
 #!/bin/bash
 # round 2, GPU call D (2 GPUs): overlapped shared-row units — parity tests + exchange cost at m = 65 / 111
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-O=gpurun_out/r2d; mkdir -p $O
+O=gpurun_out/r2e; mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "one_process_per_gpu or two_processes_sharing" > $O/pytest_sel.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_sel.log
+timeout 1500 python -m pytest tests -m gpu -x -q -s > $O/pytest_sel.log 2>&1; echo "pytest rc=$?"; grep -E "rel-L2|passed|failed" $O/pytest_sel.log | tail -8
 PORT=29531
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port"
 timeout 600 $TR $PORT bench.py --gpus 2 --refine 65 --sync-avoid off --no-also > $O/bench_n2_m65.json 2> $O/bench_n2_m65.err; echo "rc=$?"; python -c "

@@ -289,6 +289,7 @@ static void sigma_sort(std::vector<int64_t> &nodes, const std::vector<int32_t> &
     }
 }
 
+static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 static int finalize_tail(saa_plan *p, int64_t sh_pad);
 static int prepare_graphs(saa_plan *p, bool peer);
 static int finalize_device(saa_plan *p);
@@ -436,6 +437,26 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     p->D.n_rows = p->n_rows; p->D.n_slices = p->n_slices; p->D.sh_slices = p->sh_slices;
     p->D.slice_ptr = p->d_slice_ptr; p->D.val = p->d_val; p->D.col = p->d_col; p->D.dir_mask = p->d_dir;
     p->D.M = p->d_M; p->D.F = p->d_F;
+    {   // one mass value per node when every node's three DOFs hold the same bits (SAA_NODE_MASS=0 keeps the per-DOF stream)
+        const char *nm = getenv("SAA_NODE_MASS");
+        int *d_flag = nullptr, differs = 0;
+        const int64_t nn = p->n_rows / 3;
+        if (!(nm && nm[0] == '0')) {
+            CK(cudaMalloc((void **)&d_flag, sizeof(int)));
+            CK(cudaMemset(d_flag, 0, sizeof(int)));
+            saa_k_mass_check<<<nblk(nn, 256), 256>>>(nn, p->d_M, d_flag);
+            CK(cudaMemcpy(&differs, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+            cudaFree(d_flag);
+            if (!differs) {
+                double *mn = nullptr;
+                CK(cudaMalloc((void **)&mn, nn * sizeof(double)));
+                saa_k_mass_compact<<<nblk(nn, 256), 256>>>(nn, p->d_M, mn);
+                CK(cudaDeviceSynchronize());
+                cudaFree(p->d_M);
+                p->d_M = mn; p->D.M = mn; p->D.node_mass = 1;
+            }
+        }
+    }
     p->D.dt = p->dt; p->D.dt2 = p->dt2; p->D.dt_half = p->dt_half; p->D.half_alpha = p->half_alpha; p->D.alpha = p->alpha;
 
     // 3. halo: message layout, pack lists, rank-ordered source lists
@@ -551,6 +572,11 @@ extern "C" int64_t saa_plan_n_dof(const saa_plan *p) { return p ? p->n_dof : -1;
 extern "C" int64_t saa_plan_nnz(const saa_plan *p) { return p ? p->nnz : -1; }
 extern "C" int64_t saa_plan_padded_entries(const saa_plan *p) { return p ? p->padded_entries : -1; }
 extern "C" int64_t saa_plan_kernel_launches(const saa_plan *p) { return p ? p->launches : -1; }
+extern "C" int64_t saa_plan_vector_bytes(const saa_plan *p)
+{
+    // fp64 streams of one step: d0 and dn read, d1 written, F read (one value per row each) + the lumped mass (per row, or per node)
+    return p ? 4 * 8 * p->n_rows + 8 * (p->D.node_mass ? p->n_rows / 3 : p->n_rows) : -1;
+}
 extern "C" int64_t saa_plan_matrix_bytes(const saa_plan *p)
 {
     // 9 values + one column-node id per stored block, slice offsets, Dirichlet mask words
@@ -558,7 +584,6 @@ extern "C" int64_t saa_plan_matrix_bytes(const saa_plan *p)
 }
 extern "C" void *saa_plan_stream(saa_plan *p) { return p ? (void *)plan_stream(p) : nullptr; }
 
-static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 #define NEED_FINAL(p, name)                                   \
     if (!(p)) return fail(name ": null plan");                \
@@ -761,15 +786,15 @@ static int after_step(saa_plan *p, cudaStream_t st, int mode)
 // Which one is fastest depends on the schedule ptxas happens to pick; profiles/r1/kernel_variants.md has the
 // measurements behind the default.
 static void launch_step_kernel(int variant, unsigned grid, cudaStream_t st, const SaaDev &D, const SaaHaloDev &H, const double *d0,
-                               double *dn, const SaaClock *ci, SaaClock *co, int64_t slice_begin, unsigned tail_workers, unsigned count_sync)
+                               double *dn, const SaaClock *ci, SaaClock *co, int64_t slice_begin, unsigned max_waiters, unsigned count_sync)
 {
     switch (variant) {
-    case 0: saa_k_step<0, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
-    case 1: saa_k_step<0, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
-    case 2: saa_k_step<0, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
-    case 3: saa_k_step<1, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
-    case 5: saa_k_step<1, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
-    default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, tail_workers, count_sync); break;
+    case 0: saa_k_step<0, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, max_waiters, count_sync); break;
+    case 1: saa_k_step<0, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, max_waiters, count_sync); break;
+    case 2: saa_k_step<0, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, max_waiters, count_sync); break;
+    case 3: saa_k_step<1, 6><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, max_waiters, count_sync); break;
+    case 5: saa_k_step<1, 3><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, max_waiters, count_sync); break;
+    default: saa_k_step<1, 4><<<grid, 256, 0, st>>>(D, H, d0, dn, ci, co, slice_begin, max_waiters, count_sync); break;
     }
 }
 template <int STAGES, int WARPS, int BR>
@@ -995,13 +1020,13 @@ static int step_sync_nccl(saa_plan *p, int64_t n_steps)
 static void launch_peer_step(saa_plan *p, cudaStream_t st)
 {
     if (p->peer_fused && p->sh_slices > 0) {
-        // shared rows go to the last blocks to finish (ticket), in units of 256 rows; at most two waiting blocks per SM
-        // (every schedule variant keeps >= 3 resident), so blocks that have not started always find a slot
+        // n_main slice blocks + one tail block per unit of 256 shared rows; at most one WAITING tail block per SM (every
+        // schedule variant keeps >= 3 blocks per SM resident), so blocks that have not started always find a slot
         const unsigned n_main = nblk(p->n_slices, SAA_WARPS_PER_BLOCK);
         const unsigned n_units = nblk(p->H.sh_rows, 256);
-        const unsigned workers = std::max(1u, std::min(std::min(n_units, n_main), 2u * (unsigned)p->n_sms));
-        launch_step_kernel(p->kvariant, n_main, st, p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
-                           p->d_clk + (p->cur ^ 1), 0, workers, 1u);
+        const unsigned waiters = std::max(1u, std::min(n_units, (unsigned)p->n_sms));
+        launch_step_kernel(p->kvariant, n_main + n_units, st, p->D, p->Hp, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
+                           p->d_clk + (p->cur ^ 1), 0, waiters, 1u);
         p->launches++;
         p->cur ^= 1;
         return;

@@ -47,7 +47,10 @@ struct SaaDev {
     const double *val;         // block values, nine planes per block (see above)
     const int32_t *col;        // internal column NODE ids
     const uint32_t *dir_mask;  // bit (row & 31) of word (row >> 5) set: row is a Dirichlet DOF
-    const double *M;           // lumped mass, internal row order
+    const double *M;           // lumped mass, internal row order — or one value per NODE when node_mass is set (the three
+                               // DOFs of a node carry the same bits in every mesh the reference produces: row sums of
+                               // the same consistent-mass pattern, commons.py:103-107), which saves 16 B per node-step
+    int node_mass;
     const double *F;           // un-ramped load, internal row order
     double dt, dt2, dt_half, half_alpha, alpha;
 };
@@ -91,7 +94,7 @@ struct SaaHaloDev {
     unsigned int *done_ctr;                 // blocks of the pack kernel that have finished (last one raises the flags)
     unsigned long long *own_ready;          // fused step: number of steps whose own boundary forces are complete
     unsigned int *err;                      // set when a bounded wait expired (a peer never delivered)
-    unsigned int *tail_ticket;              // fused step: [0..1], [8..9] two sets of (finished blocks, claimed shared-row units); [16] fused-launch number
+    unsigned int *tail_ticket;              // fused step: [0..2], [8..10] two sets of (tail blocks gone, claimed shared-row units, waiting blocks); [16] fused-launch number
     int dbg;                                // -DSAA_DEBUG_PEER builds only (timing experiments): 1 no waits, 2 local stores,
                                             // 4 skip the shared rows, 8 treat boundary slices as interior
 };
@@ -285,21 +288,33 @@ __device__ __forceinline__ double saa_cd_update(const SaaDev &P, double Fi, doub
     return __ddiv_rn(num, den);
 }
 
+__device__ __forceinline__ void saa_finish_row_m(const SaaDev &P, int64_t row, double Fi, double M, const double *d0, double *dn_d1,
+                                                 double ramp)
+{
+    const double d1 = saa_cd_update(P, Fi, P.F[row], M, d0[row], dn_d1[row], ramp);
+    const bool clamp = (P.dir_mask[row >> 5] >> (row & 31)) & 1u;
+    dn_d1[row] = clamp ? 0.0 : d1;                                               // :20 / :32
+}
 __device__ __forceinline__ void saa_finish_row(const SaaDev &P, int64_t row, double Fi, const double *d0, double *dn_d1,
                                                double ramp)
 {
-    const double d1 = saa_cd_update(P, Fi, P.F[row], P.M[row], d0[row], dn_d1[row], ramp);
-    const bool clamp = (P.dir_mask[row >> 5] >> (row & 31)) & 1u;
-    dn_d1[row] = clamp ? 0.0 : d1;                                               // :20 / :32
+    saa_finish_row_m(P, row, Fi, P.M[P.node_mass ? row / 3 : row], d0, dn_d1, ramp);
 }
 // the three rows of the node of (slice, lane);  ADD_ZERO: f_global = 0; f_global += f (Distributed_tools.py:84-86)
 template <bool ADD_ZERO>
 __device__ __forceinline__ void saa_finish_node(const SaaDev &P, int64_t slice, int lane, const double (&s)[3], const double *d0,
                                                 double *dn_d1, double ramp)
 {
-    const int64_t row0 = 3 * (slice * 32 + lane);
+    const int64_t node = slice * 32 + lane, row0 = 3 * node;
+    double M[3];
+    if (P.node_mass) {
+        M[0] = M[1] = M[2] = P.M[node];
+    } else {
 #pragma unroll
-    for (int A = 0; A < 3; ++A) saa_finish_row(P, row0 + A, ADD_ZERO ? __dadd_rn(0.0, s[A]) : s[A], d0, dn_d1, ramp);
+        for (int A = 0; A < 3; ++A) M[A] = P.M[row0 + A];
+    }
+#pragma unroll
+    for (int A = 0; A < 3; ++A) saa_finish_row_m(P, row0 + A, ADD_ZERO ? __dadd_rn(0.0, s[A]) : s[A], M[A], d0, dn_d1, ramp);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -409,18 +424,22 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
 }
 
 // THE step kernel.  Local steps and the interior phase of the staged transports run it with sh_slices = 0 and
-// tail_workers = 0 (pure K1 over slices [slice_begin, n_slices)).  With the peer transport it is K1+K2+K3 in ONE
-// launch per synchronised step:
+// max_waiters = 0 (pure K1 over slices [slice_begin, n_slices)).  With the peer transport it is K1+K2+K3 in ONE
+// launch per synchronised step; the grid is n_main slice blocks followed by n_tail = ceil(shared rows / 256) tail blocks:
 //   * the blocks owning the boundary slices (internal order is boundary-first, so these are the lowest block
-//     indices, which the hardware dispatches first): partial forces -> own buffer and straight into the
-//     neighbours' receive areas; the warp that completes the last boundary slice raises the neighbours' arrival
-//     flags (system scope) and the local "own forces ready" flag;
+//     indices): partial forces -> own buffer and straight into the neighbours' receive areas; the warp that
+//     completes the last boundary slice raises the neighbours' arrival flags (system scope) and the local "own
+//     forces ready" flag;
 //   * the bulk of the grid streams the interior slices, overlapping the NVLink traffic;
-//   * every block that has FINISHED its slices looks at the arrival flags; once the messages are there, finishing
-//     blocks claim the shared rows in units of 256 (rank-ordered sum + update) until none is left; the last
-//     `tail_workers` finishers wait for the flags if they must.  Correctness does not depend on the order in which
-//     blocks are dispatched: waiting blocks have no slices left, and at most tail_workers (< resident capacity of
-//     the GPU) of them exist, so every block that has not run yet always finds a free slot.
+//   * the tail blocks do the rank-ordered sum and the update of the shared rows, in units of 256 rows claimed from a
+//     counter.  The hardware dispatches blocks in index order, so they normally start while the last interior
+//     blocks are still streaming, find every message already there and finish in their shadow.
+// Correctness does NOT depend on that order: a tail block that finds a message missing may wait for it (bounded)
+// only while fewer than `max_waiters` (< resident capacity of the GPU) tail blocks are waiting; otherwise it leaves,
+// and the waiting ones drain every unit that is left once the messages have arrived.  So blocks that have not run
+// yet — the boundary blocks in particular — always find a free slot, whatever the dispatch order.
+// The counters exist twice; a launch uses the set selected by the parity of a fused-launch sequence number kept in
+// device memory, and the last tail block to leave clears the other set and advances the number.
 // Same arithmetic, same order as the three-kernel sequence — one launch gap and no pipeline drain per step.
 //   count_sync: 1 on synchronised steps (advances the exchange counter), 0 on local ones.
 #ifdef SAA_DEBUG_PEER          // timing experiments only (profiling builds): results are WRONG when H.dbg != 0
@@ -431,99 +450,94 @@ __global__ void saa_k_sum_forces(int64_t n_rows, SaaHaloDev H, const double *__r
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, const double *__restrict__ d0,
                                                         double *__restrict__ dn_d1, const SaaClock *clk_in, SaaClock *clk_out,
-                                                        int64_t slice_begin, unsigned int tail_workers, unsigned int count_sync)
+                                                        int64_t slice_begin, unsigned int max_waiters, unsigned int count_sync)
 {
     const unsigned long long step = clk_in->sync_step;
     const double tn = clk_in->tn;
-    const unsigned int seq = (tail_workers != 0u) ? *((volatile const unsigned int *)(H.tail_ticket + 16)) : 0u;
     if (clk_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         clk_out->tn = __dadd_rn(tn, P.dt);
         clk_out->sync_step = step + count_sync;
         clk_out->step_idx = clk_in->step_idx + 1ull;
     }
-    {
+    const unsigned int n_units = (max_waiters != 0u) ? (unsigned int)((H.sh_rows + 255) >> 8) : 0u;
+    const unsigned int n_main = gridDim.x - n_units;
+    if (blockIdx.x < n_main) {
         const int lane = threadIdx.x & 31;
         const int64_t slice = slice_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (slice < P.n_slices) {
-            double s[3];
-            saa_node_dot<MODE, true>(P, slice, lane, d0, s);
-            if (slice < P.sh_slices && !SAA_DBG(H, 8)) {
+        if (slice >= P.n_slices) return;
+        double s[3];
+        saa_node_dot<MODE, true>(P, slice, lane, d0, s);
+        if (slice < P.sh_slices && !SAA_DBG(H, 8)) {
 #pragma unroll
-                for (int A = 0; A < 3; ++A) {
-                    const int64_t row = 3 * (slice * 32 + lane) + A;
-                    H.xbuf[row] = s[A];
-                    for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
-                        const int nb = H.dst_nb[k];
-                        if (SAA_DBG(H, 2)) H.sendbuf[H.dst_pos[k] % 3] = s[A];
-                        else H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
-                    }
+            for (int A = 0; A < 3; ++A) {
+                const int64_t row = 3 * (slice * 32 + lane) + A;
+                H.xbuf[row] = s[A];
+                for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+                    const int nb = H.dst_nb[k];
+                    if (SAA_DBG(H, 2)) H.sendbuf[H.dst_pos[k] % 3] = s[A];
+                    else H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
                 }
-                if (!SAA_DBG(H, 2)) __threadfence_system();
-                __syncwarp();
-                if (lane == 0) {
-                    const unsigned int t = atomicAdd(H.done_ctr, 1u);
-                    if (t == (unsigned int)P.sh_slices - 1u) {
-                        *H.done_ctr = 0u;
-                        __threadfence_system();
-                        for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
-                        st_release_gpu_u64(H.own_ready, step + 1ull);
-                    }
-                }
-            } else {
-                saa_finish_node<true>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
             }
+            if (!SAA_DBG(H, 2)) __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int t = atomicAdd(H.done_ctr, 1u);
+                if (t == (unsigned int)P.sh_slices - 1u) {
+                    *H.done_ctr = 0u;
+                    __threadfence_system();
+                    for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
+                    st_release_gpu_u64(H.own_ready, step + 1ull);
+                }
+            }
+        } else {
+            saa_finish_node<true>(P, slice, lane, s, d0, dn_d1, saa_ramp(tn));
         }
+        return;
     }
-    if (tail_workers == 0u) return;                   // local step / interior phase: no shared rows in this launch
-    // ---- shared rows, in units of 256.  A block that has finished its slices takes a ticket and looks at the arrival
-    // flags: if every message (and the own boundary forces) is already there it claims units until none is left, so the
-    // shared rows are normally done in the shadow of the interior stream; otherwise it leaves — unless it is one of the
-    // LAST `tail_workers` finishers, which wait (bounded) and drain whatever is left.  The counters exist twice; a
-    // launch uses the set selected by the parity of the fused-launch sequence number (device memory, read before the
-    // slices), and the very last finisher clears the other set and advances the number for the next fused launch.
+    // ---- tail blocks: shared rows
     __shared__ unsigned int s_go, s_unit;
-    unsigned int *cnt = H.tail_ticket + 8u * (seq & 1u);   // [0] finished blocks, [1] claimed units
-    const unsigned int n_units = (unsigned int)((H.sh_rows + 255) >> 8);
-    __syncthreads();
+    const unsigned int seq = *((volatile const unsigned int *)(H.tail_ticket + 16));
+    unsigned int *cnt = H.tail_ticket + 8u * (seq & 1u);   // [0] tail blocks that have left, [1] claimed units, [2] waiting blocks
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(cnt, 1u);
-        if (t == gridDim.x - 1u) {                    // every block has read `seq` by now
-            unsigned int *nxt = H.tail_ticket + 8u * ((seq & 1u) ^ 1u);
-            nxt[0] = 0u; nxt[1] = 0u;
-            __threadfence();
-            *((volatile unsigned int *)(H.tail_ticket + 16)) = seq + 1u;
-        }
-        const unsigned int claimed = *((volatile unsigned int *)(cnt + 1));
         bool ready = ld_acquire_gpu_u64(H.own_ready) >= step + 1ull;
         for (int k = 0; k < H.n_nb; ++k) ready = ready && (ld_acquire_sys_u64(H.flags + k) >= step + 1ull);
-        const bool last = t >= gridDim.x - tail_workers;
-        s_go = (claimed >= n_units || SAA_DBG(H, 4)) ? 0u : (ready || SAA_DBG(H, 1)) ? 1u : last ? 2u : 0u;
+        s_go = SAA_DBG(H, 4) ? 0u : (ready || SAA_DBG(H, 1)) ? 1u : (atomicAdd(cnt + 2, 1u) < max_waiters) ? 2u : 0u;
     }
     __syncthreads();
-    if (s_go == 0u) return;
     if (s_go == 2u) {
         if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
         if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
         __syncthreads();
     }
-    const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
-    const double ramp = saa_ramp(tn);
-    for (;;) {
-        if (threadIdx.x == 0) s_unit = atomicAdd(cnt + 1, 1u);
-        __syncthreads();
-        const unsigned int u = s_unit;
-        if (u >= n_units) break;
-        const int64_t row = (int64_t)u * 256 + threadIdx.x;
-        if (row < H.sh_rows) {
-            double Fi = 0.0;
-            for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
-                const int32_t q = H.src_pos[k];
-                const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
-                Fi = __dadd_rn(Fi, v);
+    if (s_go != 0u) {
+        const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
+        const double ramp = saa_ramp(tn);
+        for (;;) {
+            if (threadIdx.x == 0) s_unit = atomicAdd(cnt + 1, 1u);
+            __syncthreads();
+            const unsigned int u = s_unit;
+            if (u >= n_units) break;
+            const int64_t row = (int64_t)u * 256 + threadIdx.x;
+            if (row < H.sh_rows) {
+                double Fi = 0.0;
+                for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+                    const int32_t q = H.src_pos[k];
+                    const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));   // L2: written during this launch
+                    Fi = __dadd_rn(Fi, v);
+                }
+                saa_finish_row(P, row, Fi, d0, dn_d1, ramp);
             }
-            saa_finish_row(P, row, Fi, d0, dn_d1, ramp);
+            __syncthreads();                          // s_unit is rewritten in the next round
         }
-        __syncthreads();                              // s_unit is rewritten in the next round
+    }
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(cnt, 1u);
+        if (t == n_units - 1u) {                      // last tail block of this launch: every tail block has read `seq`
+            unsigned int *nxt = H.tail_ticket + 8u * ((seq & 1u) ^ 1u);
+            nxt[0] = 0u; nxt[1] = 0u; nxt[2] = 0u;
+            __threadfence();
+            *((volatile unsigned int *)(H.tail_ticket + 16)) = seq + 1u;
+        }
     }
 }
 
@@ -678,6 +692,19 @@ __global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, 
 }
 
 // ---- small data-movement kernels -----------------------------------------------------------------------
+// lumped mass per node instead of per DOF when the three DOFs of every node carry identical bits
+__global__ void saa_k_mass_check(int64_t n_nodes, const double *__restrict__ M, int *__restrict__ differs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const long long a = __double_as_longlong(M[3 * i]), b = __double_as_longlong(M[3 * i + 1]), c = __double_as_longlong(M[3 * i + 2]);
+    if (a != b || a != c) *differs = 1;
+}
+__global__ void saa_k_mass_compact(int64_t n_nodes, const double *__restrict__ M, double *__restrict__ Mn)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) Mn[i] = M[3 * i];
+}
 // external (reference local DOF order) <-> internal (boundary-first, sigma-sorted) order
 __global__ void saa_k_scatter_to_internal(int64_t n_ext, const int32_t *__restrict__ iperm, const double *__restrict__ src_ext,
                                           double *__restrict__ dst_int)

@@ -48,6 +48,7 @@ ABI = {
     "saa_plan_padded_entries": (_i64, [_vp]),
     "saa_plan_kernel_launches": (_i64, [_vp]),
     "saa_plan_matrix_bytes": (_i64, [_vp]),
+    "saa_plan_vector_bytes": (_i64, [_vp]),
     "saa_plan_set_state": (_int, [_vp, _vp, _vp, _f64]),
     "saa_plan_get_state": (_int, [_vp, _vp, _vp, _vp]),
     "saa_plan_set_state_dev": (_int, [_vp, _vp, _vp, _f64]),
@@ -229,6 +230,11 @@ class StepPlan:
     def matrix_bytes(self):
         """bytes of matrix storage the step kernel streams per time step"""
         return int(lib().saa_plan_matrix_bytes(self.h))
+
+    @property
+    def vector_bytes(self):
+        """bytes of the fp64 vector streams of one time step (d0, dn read; d1 written; F; lumped mass per DOF or per node)"""
+        return int(lib().saa_plan_vector_bytes(self.h))
 
     @property
     def kernel_launches(self):

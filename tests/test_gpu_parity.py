@@ -451,3 +451,43 @@ def test_hook_steps_from_graph_equal_per_step_launches():
     assert bits_equal(outs[0][0], outs[1][0]) and bits_equal(outs[0][1], outs[1][1])
     # recorded values of predicted steps are the table rows themselves: step 46 = row 46 - 7 = 39
     assert bits_equal(outs[0][1][-1], table[39].cpu().numpy())
+
+
+def test_mass_stream_per_node_or_per_dof_same_bits(monkeypatch):
+    """The lumped mass is streamed as one value per node when the three DOFs of every node hold identical bits (always
+    the case for the reference's row-sum lumping) and per DOF otherwise; both forms reproduce the oracle bit for bit."""
+    import scipy.sparse as sp
+    g = load_golden("beam_coarse_P3")
+    fo = oracle_module()
+    rng = np.random.default_rng(12)
+    for variant in ("node", "per_dof_forced", "per_dof_needed"):
+        if variant == "per_dof_forced":
+            monkeypatch.setenv("SAA_NODE_MASS", "0")
+        else:
+            monkeypatch.delenv("SAA_NODE_MASS", raising=False)
+        ranks = []
+        for r in g["ranks"]:
+            q = dict(r)
+            if variant == "per_dof_needed":                    # a mass that differs between the DOFs of a node
+                q["lM"] = r["lM"] * (1.0 + 0.25 * rng.random(r["lM"].shape))
+            ranks.append(q)
+        lists = [r["nodes"] for r in ranks]
+        plans = []
+        for k, r in enumerate(ranks):
+            n = r["F"].size
+            K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
+            plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), halo=maps.halo_plan(k, 3, lists), rank=k, size=3))
+        assert plans[0].vector_bytes < 40 * (plans[0].n_dof + 96) if variant == "node" else plans[0].vector_bytes >= 40 * plans[0].n_dof
+        grp = splan.PlanGroup(plans)
+        o = fo.OracleProblem(len(g["points"]), ranks, g["dt"], float(g["alpha"]))
+        for n in (1, 7, 300):
+            grp.step(n, splan.MODE_SYNC)
+            grp.synchronize()
+            o.run(n)
+            for k in range(3):
+                assert bits_equal(plans[k].d0(), o.d0(k)), (variant, n, k)
+        grp.step(40, splan.MODE_LOCAL)
+        grp.synchronize()
+        o.run(40, model=True)
+        for k in range(3):
+            assert bits_equal(plans[k].d0(), o.d0(k)), (variant, "local", k)
