@@ -477,7 +477,11 @@ def test_mass_stream_per_node_or_per_dof_same_bits(monkeypatch):
             n = r["F"].size
             K = sp.csr_matrix((r["K_data"], r["K_indices"], r["K_indptr"]), shape=(n, n))
             plans.append(splan.StepPlan(K, r["F"], r["lM"], r["dirichlet"], g["dt"], float(g["alpha"]), halo=maps.halo_plan(k, 3, lists), rank=k, size=3))
-        assert plans[0].vector_bytes < 40 * (plans[0].n_dof + 96) if variant == "node" else plans[0].vector_bytes >= 40 * plans[0].n_dof
+        vb = plans[0].vector_bytes                             # 32 B per (padded) row + the mass: 8 B per node or per row
+        if variant == "node":
+            assert (3 * vb) % 104 == 0 and (3 * vb // 104) % 96 == 0 and 3 * vb // 104 >= plans[0].n_dof
+        else:
+            assert vb % 40 == 0 and (vb // 40) % 96 == 0 and vb // 40 >= plans[0].n_dof
         grp = splan.PlanGroup(plans)
         o = fo.OracleProblem(len(g["points"]), ranks, g["dt"], float(g["alpha"]))
         for n in (1, 7, 300):
