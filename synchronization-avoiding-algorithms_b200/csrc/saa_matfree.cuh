@@ -6,7 +6,8 @@
 // the element displacement instead of being assembled (:122-150), followed by Dynamic_solver.py:13-20.  No stiffness
 // matrix exists: per time step the kernel reads the connectivity (16 B per element), the node -> element incidence
 // (4 x 4 B per element), the node coordinates (24 B per node) and the five vector streams — about 107 B per DOF-step
-// against 135 B for the node-block matrix, and 11 GB instead of 44 GB of HBM for the 104 M-DOF mesh.
+// against 400 B for the node-block matrix, and 11 GB instead of 44 GB of HBM for the 104 M-DOF mesh.  It is bound by the
+// fp64 pipe and by gather latency instead (every element is evaluated once per corner): see DESIGN.md section 4a.
 //
 // Scatter-add is made deterministic by ROW OWNERSHIP: one thread owns one node (its three rows) and walks the
 // incident tetrahedra in ascending element order, evaluating for each only the force on its own node
