@@ -176,6 +176,7 @@ struct saa_plan {
     int32_t *d_mf_inc = nullptr, *d_mf_cells = nullptr;
     double *d_mf_X = nullptr;
     int64_t mf_elems = 0, mf_lanes = 0;
+    int mf_minb = 3;                        // SAA_MF_MINB: minimum resident blocks per SM of the matrix-free kernel (register cap)
     bool matfree = false;                   // SAA_OPT_MATFREE: local steps evaluate B^T D B u_e instead of streaming the matrix
 };
 
@@ -824,8 +825,14 @@ static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, u
 static void launch_local_step(saa_plan *p, cudaStream_t st)
 {
     if (p->matfree) {
-        saa_k_step_matfree<3><<<std::max(1u, nblk(p->n_slices, SAA_WARPS_PER_BLOCK)), 32 * SAA_WARPS_PER_BLOCK, 0, st>>>(
-            p->D, p->MF, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1));
+        const unsigned g = std::max(1u, nblk(p->n_slices, SAA_WARPS_PER_BLOCK));
+        // register budget = occupancy of the gather-latency-bound kernel (SAA_MF_MINB: blocks per SM; measured in profiles/)
+        switch (p->mf_minb) {
+        case 3: saa_k_step_matfree<3><<<g, 256, 0, st>>>(p->D, p->MF, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1)); break;
+        case 5: saa_k_step_matfree<5><<<g, 256, 0, st>>>(p->D, p->MF, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1)); break;
+        case 6: saa_k_step_matfree<6><<<g, 256, 0, st>>>(p->D, p->MF, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1)); break;
+        default: saa_k_step_matfree<4><<<g, 256, 0, st>>>(p->D, p->MF, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur, p->d_clk + (p->cur ^ 1)); break;
+        }
         p->launches++;
     } else {
         launch_interior(p, st, 0, 0u, true);
@@ -1454,6 +1461,7 @@ extern "C" int saa_plan_set_matfree_dev(saa_plan *p, int64_t n_elem, const int32
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     p->mf_elems = n_elem;
+    if (const char *mb = getenv("SAA_MF_MINB")) p->mf_minb = atoi(mb);
     p->MF.slice_ptr = p->d_mf_slice_ptr; p->MF.inc = p->d_mf_inc; p->MF.cells = (const int4 *)p->d_mf_cells; p->MF.X = p->d_mf_X;
     p->MF.lmd = lmd; p->MF.mu = mu;
     return 0;

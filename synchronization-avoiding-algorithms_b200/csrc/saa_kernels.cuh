@@ -47,9 +47,10 @@ struct SaaDev {
     const double *val;         // block values, nine planes per block (see above)
     const int32_t *col;        // internal column NODE ids
     const uint32_t *dir_mask;  // bit (row & 31) of word (row >> 5) set: row is a Dirichlet DOF
-    const double *M;           // lumped mass, internal row order — or one value per NODE when node_mass is set (the three
-                               // DOFs of a node carry the same bits in every mesh the reference produces: row sums of
-                               // the same consistent-mass pattern, commons.py:103-107), which saves 16 B per node-step
+    const double *M;           // lumped mass, internal row order — or one value per NODE when node_mass is set (all three
+                               // DOFs of every node carry the same bits, checked at finalisation), which saves 16 B per
+                               // node-step; the reference's pairwise row sums (commons.py:103-107) may differ in the last
+                               // bit between the DOFs of a node and then keep the per-DOF stream
     int node_mass;
     const double *F;           // un-ramped load, internal row order
     double dt, dt2, dt_half, half_alpha, alpha;

@@ -454,8 +454,9 @@ def test_hook_steps_from_graph_equal_per_step_launches():
 
 
 def test_mass_stream_per_node_or_per_dof_same_bits(monkeypatch):
-    """The lumped mass is streamed as one value per node when the three DOFs of every node hold identical bits (always
-    the case for the reference's row-sum lumping) and per DOF otherwise; both forms reproduce the oracle bit for bit."""
+    """The lumped mass is streamed as one value per node when the three DOFs of every node hold identical bits (the device
+    set-up's lumping; the reference's pairwise row sums of the dense mass matrix can differ in the last bit between the
+    DOFs of a node, so its fixtures take the per-DOF stream) and per DOF otherwise; both forms reproduce the oracle bit for bit."""
     import scipy.sparse as sp
     g = load_golden("beam_coarse_P3")
     fo = oracle_module()
@@ -470,6 +471,8 @@ def test_mass_stream_per_node_or_per_dof_same_bits(monkeypatch):
             q = dict(r)
             if variant == "per_dof_needed":                    # a mass that differs between the DOFs of a node
                 q["lM"] = r["lM"] * (1.0 + 0.25 * rng.random(r["lM"].shape))
+            else:                                              # identical bits on the three DOFs of every node (what a per-node lumping gives;
+                q["lM"] = np.repeat(np.asarray(r["lM"]).reshape(-1, 3)[:, 0], 3).reshape(np.asarray(r["lM"]).shape)   # the fixture's row sums differ in the last bit)
             ranks.append(q)
         lists = [r["nodes"] for r in ranks]
         plans = []
