@@ -47,7 +47,8 @@ typedef struct saa_group saa_group;   /* several plans of ONE process stepped to
 #define SAA_LAUNCH_AUTO 0
 #define SAA_LAUNCH_PER_STEP 1   /* one fused kernel launch per time step                                  */
 #define SAA_LAUNCH_GRAPH 2      /* two-step CUDA graph replayed n/2 times                                 */
-#define SAA_LAUNCH_PERSISTENT 3 /* one cooperative kernel looping over all steps with grid-wide barriers  */
+#define SAA_LAUNCH_PERSISTENT 3 /* one cooperative kernel looping over all steps with grid-wide barriers:
+                                   SAA_MODE_LOCAL, and SAA_MODE_SYNC with the peer transport (small shards)   */
 
 int saa_version(void);
 const char *saa_last_error(void);

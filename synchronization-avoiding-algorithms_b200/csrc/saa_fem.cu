@@ -162,7 +162,7 @@ struct saa_plan {
     // execution
     cudaStream_t stream = nullptr;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // LOCAL-mode two-step graphs captured at cur = 0 / 1
-    int coop_blocks = 0, n_sms = 0;
+    int coop_blocks = 0, coop_blocks_sync = 0, n_sms = 0;
     int64_t launches = 0;
     saa_ncclComm_t comm = nullptr;
     saa_group *group = nullptr;
@@ -528,6 +528,8 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, p->device));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, saa_k_persistent, 32 * SAA_WARPS_PER_BLOCK, 0));
     p->coop_blocks = dev_sms * occ;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, saa_k_persistent_sync, 32 * SAA_WARPS_PER_BLOCK, 0));
+    p->coop_blocks_sync = dev_sms * occ;
     p->n_sms = dev_sms;
 
     // host copies are no longer needed
@@ -535,9 +537,9 @@ static int finalize_tail(saa_plan *p, int64_t sh_pad)
     std::vector<double>().swap(p->data); std::vector<double>().swap(p->F); std::vector<double>().swap(p->M);
     CK(cudaDeviceSynchronize());   // set-up work ran on the default stream; the plan's stream is non-blocking
     if (const char *kv = getenv("SAA_KVARIANT")) p->kvariant = atoi(kv);
-    // measured on B200 (profiles/r1/kernel_variants.md): below ~4 M rows per GPU the 3-blocks-per-SM plain schedule wins,
-    // above it the column-prefetching one with 4 blocks per SM
-    if (p->kvariant < 0) p->kvariant = (p->n_dof < 4000000) ? 2 : 4;
+    // measured on B200 (profiles/r1/kernel_variants.md, re-measured in round 2 after the mass-stream change, profiles/r2/
+    // kernel_variants_r2.md): the column-prefetching schedule with 4 blocks per SM wins at 1 M, 21 M and 104 M DOF
+    if (p->kvariant < 0) p->kvariant = 4;
     p->finalized = true;
     return prepare_graphs(p, false);
 }
@@ -1048,6 +1050,27 @@ static int step_sync_peer(saa_plan *p, int64_t n_steps, int launch)
     cudaStream_t st = p->stream;
     const bool hooks = p->hist_cap > 0;
     int64_t done = 0;
+    if (launch == SAA_LAUNCH_PERSISTENT) {
+        // one cooperative launch for all n_steps synchronised steps (small shards: no launch per step); every rank must
+        // make the same call, like any synchronised step
+        if (hooks) return fail("history hooks are not available in the persistent loop");
+        if (p->coop_blocks_sync <= 0) return fail("cooperative launch not available");
+        if (p->sh_slices == 0) return fail("saa_plan_step: the persistent synchronised loop needs an interface (this rank has none)");
+        double *a = p->d_buf[p->cur], *b = p->d_buf[p->cur ^ 1];
+        SaaClock *clk = p->d_clk + p->cur;
+        int64_t ns = n_steps;
+        void *args[] = {&p->D, &p->Hp, &a, &b, &clk, &ns};
+        const int64_t want = (p->n_slices + SAA_WARPS_PER_BLOCK - 1) / SAA_WARPS_PER_BLOCK;
+        const int blocks = (int)std::min<int64_t>(p->coop_blocks_sync, want);
+        CK(cudaLaunchCooperativeKernel((void *)saa_k_persistent_sync, dim3(blocks), dim3(32 * SAA_WARPS_PER_BLOCK), args, 0, st));
+        p->launches++;
+        if (n_steps & 1) {   // an odd number of steps swaps the buffer roles; the clock was written back to slot cur
+            CK(cudaMemcpyAsync(p->d_clk + (p->cur ^ 1), p->d_clk + p->cur, sizeof(SaaClock), cudaMemcpyDeviceToDevice, st));
+            p->cur ^= 1;
+        }
+        p->step_index += n_steps;
+        return 0;
+    }
     if (hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) return step_hook_graph(p, n_steps, SAA_MODE_SYNC);
     if (!hooks && launch != SAA_LAUNCH_PER_STEP && n_steps >= 2) {
         const int c = p->cur;

@@ -692,6 +692,86 @@ __global__ void __launch_bounds__(256) saa_k_persistent(SaaDev P, double *bufA, 
     }
 }
 
+// Persistent SYNCHRONISED loop (peer transport): one cooperative launch runs n_steps synchronised time steps — for
+// shards so small that a step is a few microseconds and the per-step launch is what limits it.  Every block is resident
+// (cooperative launch), so waiting on a neighbour's arrival flag cannot starve anybody.  Per step:
+//   * grid-stride over the slices; the boundary slices come first (lowest warp ids, first round): partial forces -> own
+//     buffer and the neighbours' receive areas, last boundary warp raises the flags (exactly as in saa_k_step);
+//   * interior slices: fused force + update;
+//   * shared rows in units of 256, grid-strided over the blocks, after the flags have arrived: rank-ordered sum + update;
+//   * one grid-wide barrier; buffers swap roles; tn and the exchange number advance in registers.
+// Same arithmetic and order as the per-step kernels — same bits.
+__global__ void __launch_bounds__(256) saa_k_persistent_sync(SaaDev P, SaaHaloDev H, double *bufA, double *bufB, SaaClock *clk_io,
+                                                             int64_t n_steps)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_units = (H.sh_rows + 255) >> 8;
+    double tn = clk_io->tn;
+    const unsigned long long sync0 = clk_io->sync_step;
+    double *d0 = bufA, *dn = bufB;
+    for (int64_t it = 0; it < n_steps; ++it) {
+        const unsigned long long step = sync0 + (unsigned long long)it;
+        const double ramp = saa_ramp(tn);
+        for (int64_t slice = warp0; slice < P.n_slices; slice += nwarps) {
+            double s[3];
+            saa_node_dot<SAA_DOT_MODE, false>(P, slice, lane, d0, s);
+            if (slice < P.sh_slices) {
+#pragma unroll
+                for (int A = 0; A < 3; ++A) {
+                    const int64_t row = 3 * (slice * 32 + lane) + A;
+                    H.xbuf[row] = s[A];
+                    for (int64_t k = H.dst_ptr[row]; k < H.dst_ptr[row + 1]; ++k) {
+                        const int nb = H.dst_nb[k];
+                        H.peer_recv[nb][(int64_t)(step & 1ull) * H.peer_stride[nb] + H.dst_pos[k]] = s[A];
+                    }
+                }
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned int t = atomicAdd(H.done_ctr, 1u);
+                    if (t == (unsigned int)P.sh_slices - 1u) {
+                        *H.done_ctr = 0u;
+                        __threadfence_system();
+                        for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
+                        st_release_gpu_u64(H.own_ready, step + 1ull);
+                    }
+                }
+            } else {
+                saa_finish_node<true>(P, slice, lane, s, d0, dn, ramp);
+            }
+        }
+        if ((int64_t)blockIdx.x < n_units) {                    // this block owns shared-row units of this step
+            if (threadIdx.x < H.n_nb) saa_wait_ge<true>(H.flags + threadIdx.x, step + 1ull, H.err);
+            if (threadIdx.x == 255) saa_wait_ge<false>(H.own_ready, step + 1ull, H.err);
+            __syncthreads();
+            const double *recv = H.recv + (int64_t)(step & 1ull) * H.recv_stride;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int64_t row = u * 256 + threadIdx.x;
+                if (row < H.sh_rows) {
+                    double Fi = 0.0;
+                    for (int64_t k = H.src_ptr[row]; k < H.src_ptr[row + 1]; ++k) {
+                        const int32_t q = H.src_pos[k];
+                        const double v = (q < H.sh_rows) ? __ldcg(H.xbuf + q) : __ldcg(recv + (q - H.sh_rows));
+                        Fi = __dadd_rn(Fi, v);
+                    }
+                    saa_finish_row(P, row, Fi, d0, dn, ramp);
+                }
+            }
+        }
+        tn = __dadd_rn(tn, P.dt);
+        double *t = d0; d0 = dn; dn = t;
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        clk_io->tn = tn;
+        clk_io->sync_step = sync0 + (unsigned long long)n_steps;
+        clk_io->step_idx += (unsigned long long)n_steps;
+    }
+}
+
 // ---- small data-movement kernels -----------------------------------------------------------------------
 // lumped mass per node instead of per DOF when the three DOFs of every node carry identical bits
 __global__ void saa_k_mass_check(int64_t n_nodes, const double *__restrict__ M, int *__restrict__ differs)

@@ -76,6 +76,14 @@ if transport == "peer":
             assert ref is None or bits_equal(got, ref), (golden, fused, launch, rank)
             ref = got
     pl.set_option(splan.OPT_PEER_FUSED, 1)
+    if not shared_gpu:                                   # cooperative persistent synchronised loop: one launch for all steps
+        for n_steps in (9, 4):
+            pl.set_state(d0, dn, tn)
+            pl.step(n_steps, splan.MODE_SYNC, splan.LAUNCH_PERSISTENT)
+            if n_steps == 4:
+                pl.step(5, splan.MODE_SYNC)              # continues seamlessly with the per-step form (odd / even buffer parity)
+            pl.synchronize()
+            assert bits_equal(pl.d0(), ref), (golden, "persistent", n_steps, rank)
 # interleave un-synchronised steps (MODEL=True) and a per-step launch; all ranks stay in lockstep
 pl.step(5, splan.MODE_LOCAL)
 pl.step(3, splan.MODE_SYNC, splan.LAUNCH_PER_STEP)
