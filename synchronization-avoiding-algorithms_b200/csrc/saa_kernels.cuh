@@ -110,6 +110,12 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// relaxed system-scope store: together with the __threadfence_system() in front of it this is a release pattern
+// (fence.acq_rel.sys ; st.relaxed.sys), which publishes to SEVERAL flags with ONE fence instead of one per st.release
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
 {
     unsigned long long v;
@@ -362,8 +368,8 @@ __global__ void __launch_bounds__(256) saa_k_boundary(SaaDev P, SaaHaloDev H, co
             const unsigned int t = atomicAdd(H.done_ctr, 1u);
             if (t == gridDim.x - 1) {
                 *H.done_ctr = 0u;                    // re-arm for the next step (next launch is stream-ordered)
-                __threadfence_system();
-                for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
+                __threadfence_system();              // one release fence for all flags below
+                for (int k = 0; k < H.n_nb; ++k) st_relaxed_sys_u64(H.peer_flag[k], step + 1ull);
             }
         }
     }
@@ -485,9 +491,9 @@ __global__ void __launch_bounds__(256, MINB) saa_k_step(SaaDev P, SaaHaloDev H, 
                 const unsigned int t = atomicAdd(H.done_ctr, 1u);
                 if (t == (unsigned int)P.sh_slices - 1u) {
                     *H.done_ctr = 0u;
-                    __threadfence_system();
-                    for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
-                    st_release_gpu_u64(H.own_ready, step + 1ull);
+                    __threadfence_system();          // one release fence for all flags below
+                    for (int k = 0; k < H.n_nb; ++k) st_relaxed_sys_u64(H.peer_flag[k], step + 1ull);
+                    st_relaxed_sys_u64(H.own_ready, step + 1ull);
                 }
             }
         } else {
@@ -734,9 +740,9 @@ __global__ void __launch_bounds__(256) saa_k_persistent_sync(SaaDev P, SaaHaloDe
                     const unsigned int t = atomicAdd(H.done_ctr, 1u);
                     if (t == (unsigned int)P.sh_slices - 1u) {
                         *H.done_ctr = 0u;
-                        __threadfence_system();
-                        for (int k = 0; k < H.n_nb; ++k) st_release_sys_u64(H.peer_flag[k], step + 1ull);
-                        st_release_gpu_u64(H.own_ready, step + 1ull);
+                        __threadfence_system();      // one release fence for all flags below
+                        for (int k = 0; k < H.n_nb; ++k) st_relaxed_sys_u64(H.peer_flag[k], step + 1ull);
+                        st_relaxed_sys_u64(H.own_ready, step + 1ull);
                     }
                 }
             } else {
