@@ -661,29 +661,40 @@ def main():
         ms_local = float(np.median(rl)) / steps
 
     # ---- end to end through the reference-facing host call -----------------------------------------
-    d0, dn, tn = pl.get_state()
-    h0 = torch.from_numpy(d0).pin_memory().numpy()
-    hn = torch.from_numpy(dn).pin_memory().numpy()
-    h1 = torch.empty(n_dof_local, dtype=torch.float64).pin_memory().numpy()
-    del d0, dn
+    # the loop of Data_prepare.py:223-235 with host arrays: d1 comes back in page-locked memory owned by the plan's pool
+    # and is rotated into d_0 / d_n, so from the second call on every vector that crosses PCIe is pinned
+    s0, sn, tn0 = pl.get_state()
+    h0, hn, tn = s0, sn, tn0
     for _ in range(3):
-        pl.step_host(h0, hn, tn, mode, out=h1)
-        h0, hn, h1 = h1, h0, hn
+        h1 = pl.step_host(h0, hn, tn, mode)
+        hn, h0 = h0, h1
         tn = tn + dtv
     barrier()
     skipped0 = getattr(pl, "host_uploads_skipped", 0)
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        pl.step_host(h0, hn, tn, mode, out=h1)       # d1 lands in host memory every call
-        h0, hn, h1 = h1, h0, hn                      # d_n = d_0; d_0 = d1 (Data_prepare.py:233-234)
+        h1 = pl.step_host(h0, hn, tn, mode)          # d1 lands in host memory every call
+        hn, h0 = h0, h1                              # d_n = d_0; d_0 = d1 (Data_prepare.py:233-234)
         tn = tn + dtv
     pl.synchronize()
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - w0) * 1e3)   # the call is synchronous: wall clock covers copies + kernels
     dn_skipped = getattr(pl, "host_uploads_skipped", 0) - skipped0
     h2d = (8 * n_dof_local * (2 * e2e_steps - dn_skipped)) / e2e_steps
+    pipe_k, _, pipe_need = pl.host_pipe_info(mode)
+    pipe = {"chunks": int(pipe_k), "max_lag_chunks": int(max(pipe_need - np.arange(pipe_k))) if pipe_k else None,
+            "pinned_result_buffers": len(getattr(pl, "_pinned_pool", []))}
+    # the host-call results against the device-resident steps from the same state: bit for bit
+    pl.set_state(s0, sn, tn0)
+    pl.step(3 + e2e_steps, mode)
+    pl.synchronize()
+    e2e_same = bool(np.array_equal(pl.d0().view(np.uint64), h0.view(np.uint64)))
+    if world > 1:
+        tt = torch.tensor([1.0 if e2e_same else 0.0], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        e2e_same = bool(tt.item() == 1.0)
+    del h0, hn, h1, s0, sn
     clocks = sampler.stop() if sampler else None
-    del h0, hn, h1
 
     # ---- cross-path check on the timed mesh (N > 1, peer transport) ----------------------------------
     if parity is not None and transport == "peer":
@@ -767,8 +778,10 @@ def main():
             "e2e": {"value": n_dof_global * e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * n_dof_local,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "dn_uploads_skipped": dn_skipped,
-                    "call": "saa_step_host_ex (one parallel_explicit_solver_dis_pre evaluation per call, pinned host d0/dn in, d1 out; "
-                            "dn = the previous call's d0 array is recognised and not uploaded again)"},
+                    "pipeline": pipe, "bit_identical_to_resident_steps": e2e_same,
+                    "call": "saa_step_host_ex (one parallel_explicit_solver_dis_pre evaluation per call, host d0/dn in, d1 out in page-locked "
+                            "memory that the caller rotates into d0/dn; dn = the previous call's d0 array is recognised and not uploaded "
+                            "again; upload, step and download of the row chunks overlap on three streams)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -204,6 +204,23 @@ int saa_step_host(saa_plan *plan, const double *d0_host, const double *dn_host, 
 #define SAA_HOST_DN_IS_PREVIOUS_D0 1
 int saa_step_host_ex(saa_plan *plan, const double *d0_host, const double *dn_host, double tn, int mode,
                      double *d1_host, int flags);
+/*
+ * How saa_step_host[_ex] runs for `mode` on this plan.  Plans of >= 4 MiB per vector cut the call into K <= 32 chunks of
+ * caller-order rows and overlap the upload of d0, the step over the rows whose inputs have arrived and the download
+ * of d1 (three streams; PCIe is full duplex) — same kernels, every row computed once, same bits as the plain
+ * sequence.  n_chunks = 0: the plain upload-step-download sequence is used (small plans, hooks, matrix-free mode, or
+ * SAA_STEP_HOST_PIPELINE=0 in the environment; SAA_STEP_HOST_PIPELINE=K forces K chunks).  slice_end[c] / need_upload[c]
+ * (capacity `cap`, may be NULL): compute chunk c ends at this internal slice and starts once the uploads of chunks
+ * <= need_upload[c] are in — need_upload[c] - c is the pipeline lag the memory layout allows.
+ */
+int saa_plan_host_pipe_info(saa_plan *plan, int mode, int *n_chunks, int64_t *slice_end, int32_t *need_upload, int cap);
+/*
+ * Page-locked host memory for the d0 / dn / d1 vectors of saa_step_host[_ex] (the reference allocates them with
+ * numpy, Data_prepare.py:215-217 and Dynamic_solver.py:18): copies from / to such memory are asynchronous and run at
+ * the full PCIe rate.  Any host pointer is accepted by saa_step_host; pageable ones are staged by the CUDA driver.
+ */
+void *saa_host_alloc(int64_t bytes);
+int saa_host_free(void *ptr);
 
 /*
  * Record rows of the solution on the device every `save_every` steps (the d1_save / d_sol_shared

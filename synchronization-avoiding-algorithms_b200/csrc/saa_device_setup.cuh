@@ -16,17 +16,6 @@
 #include <thrust/sequence.h>
 #include <thrust/sort.h>
 
-struct DevBuf {   // RAII scratch
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes)
-    {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
-        if (e != cudaSuccess) return fail("cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
-        return 0;
-    }
-    template <class T> T *as() { return (T *)p; }
-};
 
 // ---- kernels of the device finalize (node-block sliced ELL, same layout as the host path) ---------------------
 // three-way merge over the (sorted) rows 3e, 3e+1, 3e+2 of node e: visits the distinct column nodes ascending

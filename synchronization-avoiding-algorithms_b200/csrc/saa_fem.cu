@@ -169,6 +169,19 @@ struct saa_plan {
     cudaEvent_t ev_msg = nullptr;
     bool in_split_step = false;             // between saa_plan_step_begin_host and saa_plan_step_end_host
     int64_t state_epoch = 1, host_epoch = 0; // saa_step_host_ex: the device still holds the previous call's d0 iff equal
+    // pipelined host call (saa_step_host_ex): chunks of external rows; upload / compute / download overlap
+    struct HostPipe {
+        int state = 0;                        // 0 not built yet, 1 usable, -1 not applicable
+        int64_t first_slice = 0;              // slices below are boundary slices (table 1) and not part of the chunks
+        std::vector<int64_t> row_off;         // [K+1] external row offsets of the chunks
+        std::vector<int64_t> slice_end;       // [K] compute chunk c = internal slices [slice_end[c-1], slice_end[c])
+        std::vector<int> need_upload;         // [K] compute chunk c needs the uploads of chunks <= need_upload[c]
+        std::vector<char> has_shared;         // [K] table 1: chunk holds shared rows (downloaded after the shared-row update)
+        int need_boundary = -1;               // table 1: the boundary slices need the uploads of chunks <= this
+    } hp[2];                                  // [0] local steps, [1] synchronised steps of a plan with neighbours
+    std::vector<cudaEvent_t> hp_ev_up, hp_ev_cmp;
+    cudaEvent_t hp_ev_final = nullptr;
+    cudaStream_t hp_s_in = nullptr, hp_s_out = nullptr;
     double *d_force = nullptr;              // [2 * n_rows] scratch of the stand-alone force synchronisation
     // matrix-free mode (K5, saa_plan_set_matfree_dev)
     SaaMatFreeDev MF{};
@@ -271,6 +284,18 @@ extern "C" int saa_plan_set_node_order(saa_plan *p, const int32_t *order, int64_
     p->node_order.assign(order, order + n_nodes);
     return 0;
 }
+
+struct DevBuf {   // RAII scratch
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+        return 0;
+    }
+    template <class T> T *as() { return (T *)p; }
+};
 
 template <class T>
 static int upload(T **dptr, const std::vector<T> &h)
@@ -565,6 +590,11 @@ extern "C" int saa_plan_destroy(saa_plan *p)
             if (q) cudaFree(q);
         if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
         if (p->ev_msg) cudaEventDestroy(p->ev_msg);
+        for (cudaEvent_t e : p->hp_ev_up) cudaEventDestroy(e);
+        for (cudaEvent_t e : p->hp_ev_cmp) cudaEventDestroy(e);
+        if (p->hp_ev_final) cudaEventDestroy(p->hp_ev_final);
+        if (p->hp_s_in) cudaStreamDestroy(p->hp_s_in);
+        if (p->hp_s_out) cudaStreamDestroy(p->hp_s_out);
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;
@@ -810,15 +840,17 @@ static void launch_stream(saa_plan *p, cudaStream_t st, const SaaDev &D, int64_t
     p->launches++;
 }
 // K1 only: slices [slice_begin, n_slices) as interior rows (no interface handling inside the kernel)
-static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, unsigned count_sync, bool advance_clock)
+static void launch_interior(saa_plan *p, cudaStream_t st, int64_t slice_begin, unsigned count_sync, bool advance_clock, int64_t slice_end = -1)
 {
     SaaDev D = p->D;
     D.sh_slices = 0;
+    if (slice_end < 0) slice_end = p->n_slices;
     if (p->kvariant >= 6 && p->n_slices > slice_begin) {       // cp.async streaming kernels, persistent grid
         launch_stream<3, 24, 1>(p, st, D, slice_begin, count_sync, advance_clock);   // the fastest streaming configuration measured
         return;
     }
-    const unsigned n_main = std::max(1u, nblk(p->n_slices - slice_begin, SAA_WARPS_PER_BLOCK));
+    // slices [slice_begin, slice_end): slice_end - slice_begin is a multiple of the warps per block unless slice_end = n_slices
+    const unsigned n_main = std::max(1u, nblk(slice_end - slice_begin, SAA_WARPS_PER_BLOCK));
     launch_step_kernel(p->kvariant, n_main, st, D, p->H, p->d_buf[p->cur], p->d_buf[p->cur ^ 1], p->d_clk + p->cur,
                        advance_clock ? p->d_clk + (p->cur ^ 1) : nullptr, slice_begin, 0u, count_sync);
     p->launches++;
@@ -1002,21 +1034,28 @@ static void sync_phase_shared(saa_plan *p, cudaStream_t st)
     p->cur ^= 1;
 }
 
+// the neighbour messages of one synchronised step through NCCL (grouped send / receive pairs on the plan's stream)
+static int nccl_exchange(saa_plan *p, cudaStream_t st)
+{
+    const int n_nb = (int)p->nb_rank.size();
+    if (n_nb > 0) {
+        NCK(g_nccl.GroupStart());
+        for (int k = 0; k < n_nb; ++k) {
+            const size_t cnt = (size_t)(p->msg_off[k + 1] - p->msg_off[k]);
+            NCK(g_nccl.Send(p->d_send + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
+            NCK(g_nccl.Recv(p->d_recv + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
+        }
+        NCK(g_nccl.GroupEnd());
+    }
+    return 0;
+}
+
 static int step_sync_nccl(saa_plan *p, int64_t n_steps)
 {
     cudaStream_t st = p->stream;
-    const int n_nb = (int)p->nb_rank.size();
     for (int64_t s = 0; s < n_steps; ++s) {
         sync_phase_boundary(p, st);
-        if (n_nb > 0) {
-            NCK(g_nccl.GroupStart());
-            for (int k = 0; k < n_nb; ++k) {
-                const size_t cnt = (size_t)(p->msg_off[k + 1] - p->msg_off[k]);
-                NCK(g_nccl.Send(p->d_send + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
-                NCK(g_nccl.Recv(p->d_recv + p->msg_off[k], cnt, SAA_NCCL_DOUBLE, p->nb_rank[k], p->comm, st));
-            }
-            NCK(g_nccl.GroupEnd());
-        }
+        if (nccl_exchange(p, st)) return -1;
         sync_phase_interior(p, st);
         sync_phase_shared(p, st);
         if (after_step(p, st, SAA_MODE_SYNC)) return -1;
@@ -1158,6 +1197,232 @@ extern "C" int saa_plan_synchronize(saa_plan *p)
     return 0;
 }
 
+// ---- pipelined host call ------------------------------------------------------------------------------------------
+// The reference-facing call moves d0 up and d1 down over PCIe around ONE step; done one after the other that is
+// upload + step + download.  PCIe is full duplex and a row of the step only needs the d0 entries of its own column
+// window, so the call is cut into K chunks of EXTERNAL rows and run as a three-stage pipeline on three streams:
+//   upload  c : rows [row_off[c], row_off[c+1]) of d0 (and dn) -> staging -> internal order            (stream s_in)
+//   compute c : internal slices [slice_end[c-1], slice_end[c]) — every slice holding a row of the chunks <= c —
+//               after the uploads of all chunks its rows and column nodes live in (need_upload[c])     (plan stream)
+//   download c: rows of chunk c of d1 -> external order -> host, after compute c                        (stream s_out)
+// Same kernels on the same data, every row computed exactly once: same bits as the plain call.  With a layout whose
+// column windows span everything (random node order) need_upload = K-1 and it degenerates to upload-all-then-compute.
+// Synchronised steps of a multi-partition plan (table 1) chunk the INTERIOR slices the same way; the boundary slices
+// (K2: partial forces -> neighbours) are launched as soon as the chunks they read have arrived, the shared-row update
+// (K3) after the last interior chunk, and the chunks that hold shared rows are downloaded after it.
+__global__ void saa_k_hp_inverse(int64_t n_ext_nodes, const int32_t *__restrict__ iperm, int32_t *__restrict__ ext_of_int)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_ext_nodes) ext_of_int[iperm[3 * e] / 3] = (int32_t)e;
+}
+// per slice: largest external node among its own nodes and among own + column nodes of its blocks (-1: all-padding slice)
+__global__ void saa_k_hp_slice_reach(SaaDev P, const int32_t *__restrict__ ext_of_int, int32_t *__restrict__ reach_own, int32_t *__restrict__ reach_col)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slice >= P.n_slices) return;
+    const int32_t own = ext_of_int[slice * 32 + lane];
+    int32_t mc = own;
+    if (own >= 0) {                                              // padding lanes point at themselves
+        const int64_t beg = P.slice_ptr[slice];
+        const int len = (int)((P.slice_ptr[slice + 1] - beg) >> 5);
+        for (int j = 0; j < len; ++j) mc = max(mc, ext_of_int[P.col[beg + 32 * j + lane]]);
+    }
+    int32_t mo = own;
+    for (int o = 16; o > 0; o >>= 1) {
+        mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+        mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    }
+    if (lane == 0) { reach_own[slice] = mo; reach_col[slice] = mc; }
+}
+
+// table 0: every slice as an interior slice (local steps); table 1: synchronised steps of a plan with an interface
+static int host_pipe_build(saa_plan *p, int table)
+{
+    saa_plan::HostPipe &h = p->hp[table];
+    h.state = -1;
+    const char *env = getenv("SAA_STEP_HOST_PIPELINE");
+    if (env && env[0] == '0') { h.state = 0; return 0; }        // switched off for now: decide again at the next call
+    const int64_t nn = p->n_dof / 3;
+    int K = (int)std::min<int64_t>(32, (p->n_dof * 8) / (2 << 20));      // chunks of at least 2 MiB (below that the launches cost more than the overlap gains)
+    if (env && atoi(env) > 1) K = (int)std::min<int64_t>(std::min(atoi(env), 64), nn);
+    if (K < 2) return 0;
+    const int64_t sb = table == 1 ? p->sh_slices : 0;            // first slice handled as an interior slice
+    DevBuf inv, r_own, r_col;
+    const int64_t n_int = p->n_rows / 3;
+    if (inv.alloc(n_int * sizeof(int32_t)) || r_own.alloc(p->n_slices * sizeof(int32_t)) || r_col.alloc(p->n_slices * sizeof(int32_t))) return -1;
+    CK(cudaMemset(inv.p, 0xff, n_int * sizeof(int32_t)));                // -1: padding node
+    saa_k_hp_inverse<<<nblk(nn, 256), 256>>>(nn, p->d_iperm, inv.as<int32_t>());
+    saa_k_hp_slice_reach<<<nblk(p->n_slices, SAA_WARPS_PER_BLOCK), 32 * SAA_WARPS_PER_BLOCK>>>(p->D, inv.as<int32_t>(), r_own.as<int32_t>(), r_col.as<int32_t>());
+    CK(cudaGetLastError());
+    std::vector<int32_t> own(p->n_slices), col(p->n_slices);
+    CK(cudaMemcpy(own.data(), r_own.p, p->n_slices * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(col.data(), r_col.p, p->n_slices * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    // chunks of external nodes of equal size
+    std::vector<int64_t> node_off(K + 1);
+    for (int c = 0; c <= K; ++c) node_off[c] = (nn * c) / K;
+    auto chunk_of = [&](int64_t e) { return (int)(std::upper_bound(node_off.begin(), node_off.end(), e) - node_off.begin()) - 1; };
+    // compute chunk c must cover every interior slice that holds an external node of the chunks <= c: attribute each slice
+    // to the chunk of its SMALLEST external node (the earliest download that needs it) and take running maxima
+    h.first_slice = sb;
+    h.slice_end.assign(K, 0);
+    h.need_upload.assign(K, 0);
+    h.has_shared.assign(K, 0);
+    h.need_boundary = -1;
+    std::vector<int32_t> min_own(p->n_slices, INT32_MAX);
+    for (int64_t e = 0; e < nn; ++e) {
+        const int64_t s = (p->iperm_h[3 * e] / 3) >> 5;
+        min_own[s] = std::min<int32_t>(min_own[s], (int32_t)e);
+        if (s < sb) h.has_shared[chunk_of(e)] = 1;
+    }
+    std::vector<int64_t> last_slice(K, -1);
+    for (int64_t s = sb; s < p->n_slices; ++s)
+        if (own[s] >= 0) {
+            const int c = chunk_of(min_own[s]);
+            last_slice[c] = std::max(last_slice[c], s);
+        }
+    int64_t run = sb;
+    for (int c = 0; c < K; ++c) {
+        run = std::max(run, last_slice[c] + 1);
+        // ranges start at sb and have a whole number of thread blocks' worth of slices, except the last one
+        const int64_t end = (c == K - 1) ? p->n_slices
+                                         : std::min<int64_t>(p->n_slices, sb + (run - sb + SAA_WARPS_PER_BLOCK - 1) / SAA_WARPS_PER_BLOCK * SAA_WARPS_PER_BLOCK);
+        h.slice_end[c] = end;
+        run = end;
+    }
+    for (int64_t s = sb; s < p->n_slices; ++s)                   // every slice is finished before the first download that reads it
+        if (own[s] >= 0 && s >= h.slice_end[chunk_of(min_own[s])]) return fail("host_pipe_build: inconsistent chunk table");
+    for (int c = 0; c < K; ++c) {
+        int32_t reach = -1;
+        for (int64_t s = (c ? h.slice_end[c - 1] : sb); s < h.slice_end[c]; ++s) reach = std::max(reach, col[s]);
+        h.need_upload[c] = std::max(reach >= 0 ? chunk_of(reach) : 0, c ? h.need_upload[c - 1] : 0);
+    }
+    if (sb > 0) {
+        int32_t reach = -1;
+        for (int64_t s = 0; s < sb; ++s) reach = std::max(reach, col[s]);
+        h.need_boundary = reach >= 0 ? chunk_of(reach) : 0;
+    }
+    h.row_off.resize(K + 1);
+    for (int c = 0; c <= K; ++c) h.row_off[c] = 3 * node_off[c];
+    if (!p->hp_s_in) {
+        CK(cudaStreamCreateWithFlags(&p->hp_s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&p->hp_s_out, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&p->hp_ev_final, cudaEventDisableTiming));
+    }
+    while ((int)p->hp_ev_up.size() < K) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        p->hp_ev_up.push_back(a); p->hp_ev_cmp.push_back(b);
+    }
+    CK(cudaDeviceSynchronize());
+    h.state = 1;
+    return 0;
+}
+
+static int host_pipe_step(saa_plan *p, int table, const double *d0, const double *dn, double tn, double *d1, bool keep_dn)
+{
+    saa_plan::HostPipe &h = p->hp[table];
+    const int K = (int)h.slice_end.size();
+    const bool sync = table == 1;
+    const unsigned count_sync = sync ? 1u : 0u;
+    cudaStream_t st = p->stream, s_in = p->hp_s_in, s_out = p->hp_s_out;
+    CK(cudaStreamSynchronize(st));                               // earlier work of the plan (other entry points use this stream)
+    p->state_epoch += 2;                                         // state upload + step, like the plain call
+    CK(cudaMemcpyAsync(&p->d_clk[p->cur].tn, &tn, sizeof(double), cudaMemcpyHostToDevice, s_in));
+    double *b0 = p->d_buf[p->cur], *b1 = p->d_buf[p->cur ^ 1];
+    double *stage_dn = p->d_stage + p->n_dof, *stage_out = p->d_stage + 2 * p->n_dof;
+    for (int c = 0; c < K; ++c) {                                // stage 1: uploads, in order
+        const int64_t off = h.row_off[c], cnt = h.row_off[c + 1] - off;
+        CK(cudaMemcpyAsync(p->d_stage + off, d0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        saa_k_scatter_to_internal<<<nblk(cnt, 256), 256, 0, s_in>>>(cnt, p->d_iperm + off, p->d_stage + off, b0);
+        p->launches++;
+        if (!keep_dn) {
+            CK(cudaMemcpyAsync(stage_dn + off, dn + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s_in));
+            saa_k_scatter_to_internal<<<nblk(cnt, 256), 256, 0, s_in>>>(cnt, p->d_iperm + off, stage_dn + off, b1);
+            p->launches++;
+        }
+        CK(cudaEventRecord(p->hp_ev_up[c], s_in));
+    }
+    auto download = [&](int c) -> int {                          // stage 3: d1 of the chunk's rows -> external order -> host
+        const int64_t off = h.row_off[c], cnt = h.row_off[c + 1] - off;
+        saa_k_gather_to_external<<<nblk(cnt, 256), 256, 0, s_out>>>(cnt, p->d_iperm + off, b1, stage_out + off);
+        p->launches++;
+        CK(cudaMemcpyAsync(d1 + off, stage_out + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        return 0;
+    };
+    int waited = -1;
+    auto wait_uploads = [&](int c) -> int {
+        if (c > waited) { CK(cudaStreamWaitEvent(st, p->hp_ev_up[c], 0)); waited = c; }
+        return 0;
+    };
+    bool boundary_done = !(sync && p->sh_slices > 0);
+    for (int c = 0; c < K; ++c) {                                // stage 2: the step, slice range by slice range
+        if (!boundary_done && (h.need_upload[c] >= h.need_boundary || c == K - 1)) {
+            if (wait_uploads(h.need_boundary)) return -1;
+            sync_phase_boundary(p, st);                          // K2: partial forces of the shared rows -> neighbours
+            if (!use_peer(p) && nccl_exchange(p, st)) return -1;
+            boundary_done = true;
+        }
+        if (wait_uploads(h.need_upload[c])) return -1;
+        const int64_t s0 = c ? h.slice_end[c - 1] : h.first_slice, s1 = h.slice_end[c];
+        if (s1 > s0) launch_interior(p, st, s0, count_sync, c == 0, s1);
+        else if (c == 0) launch_interior(p, st, p->n_slices, count_sync, true, p->n_slices);   // no slice, the clock only
+        CK(cudaEventRecord(p->hp_ev_cmp[c], st));
+        if (!(sync && h.has_shared[c])) {
+            CK(cudaStreamWaitEvent(s_out, p->hp_ev_cmp[c], 0));
+            if (download(c)) return -1;
+        }
+    }
+    if (sync) {
+        sync_phase_shared(p, st);                                // K3: rank-ordered sums + update of the shared rows; swaps the levels
+        CK(cudaEventRecord(p->hp_ev_final, st));
+        CK(cudaStreamWaitEvent(s_out, p->hp_ev_final, 0));
+        for (int c = 0; c < K; ++c)
+            if (h.has_shared[c] && download(c)) return -1;
+    } else {
+        p->cur ^= 1;
+    }
+    CK(cudaGetLastError());
+    p->step_index++;
+    CK(cudaStreamSynchronize(s_out));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(s_in));
+    return 0;
+}
+
+extern "C" int saa_plan_host_pipe_info(saa_plan *p, int mode, int *n_chunks, int64_t *slice_end, int32_t *need_upload, int cap)
+{
+    NEED_FINAL(p, "saa_plan_host_pipe_info");
+    if (!n_chunks) return fail("saa_plan_host_pipe_info: null argument");
+    CK(cudaSetDevice(p->device));
+    const int table = (mode == SAA_MODE_SYNC && p->size > 1) ? 1 : 0;
+    if (p->hp[table].state == 0 && host_pipe_build(p, table)) return -1;
+    const saa_plan::HostPipe &h = p->hp[table];
+    const int K = h.state == 1 ? (int)h.slice_end.size() : 0;
+    *n_chunks = K;
+    if (K > 0 && slice_end && need_upload) {
+        if (cap < K) return fail("saa_plan_host_pipe_info: capacity %d < %d chunks", cap, K);
+        for (int c = 0; c < K; ++c) { slice_end[c] = h.slice_end[c]; need_upload[c] = h.need_upload[c]; }
+    }
+    return 0;
+}
+
+// pinned (page-locked) host memory for the vectors of saa_step_host[_ex]: asynchronous, full-speed PCIe copies
+extern "C" void *saa_host_alloc(int64_t bytes)
+{
+    void *q = nullptr;
+    if (bytes <= 0) { fail("saa_host_alloc: non-positive size"); return nullptr; }
+    cudaError_t e = cudaHostAlloc(&q, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail("cudaHostAlloc(%lld) -> %s", (long long)bytes, cudaGetErrorString(e)); return nullptr; }
+    return q;
+}
+extern "C" int saa_host_free(void *q)
+{
+    if (q) CK(cudaFreeHost(q));
+    return 0;
+}
+
 extern "C" int saa_step_host_ex(saa_plan *p, const double *d0, const double *dn, double tn, int mode, double *d1, int flags)
 {
     NEED_FINAL(p, "saa_step_host");
@@ -1169,6 +1434,18 @@ extern "C" int saa_step_host_ex(saa_plan *p, const double *d0, const double *dn,
     // previous one, which the device still holds in the other displacement level (the step overwrote the OLD dn with
     // d1 and swapped).  Valid only while nothing else touched the plan's state since that call.
     const bool keep_dn = (flags & SAA_HOST_DN_IS_PREVIOUS_D0) && p->host_epoch == p->state_epoch;
+    const bool local = mode == SAA_MODE_LOCAL || (mode == SAA_MODE_SYNC && p->size == 1);
+    const bool sync = mode == SAA_MODE_SYNC && p->size > 1 && (use_peer(p) || p->comm);
+    const char *pipe_env = getenv("SAA_STEP_HOST_PIPELINE");  // "0": plain sequence (checked per call); K > 1: K chunks (read when the table is built)
+    if ((local || sync) && !needs_hooks(p, mode) && !p->matfree && p->kvariant < 6 && !(pipe_env && pipe_env[0] == '0')) {
+        const int table = sync ? 1 : 0;
+        if (p->hp[table].state == 0 && host_pipe_build(p, table)) return -1;
+        if (p->hp[table].state == 1) {
+            if (host_pipe_step(p, table, d0, dn, tn, d1, keep_dn)) return -1;
+            p->host_epoch = p->state_epoch;
+            return keep_dn ? 1 : 0;
+        }
+    }
     CK(cudaMemcpyAsync(p->d_stage, d0, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
     if (!keep_dn) CK(cudaMemcpyAsync(p->d_stage + p->n_dof, dn, p->n_dof * sizeof(double), cudaMemcpyHostToDevice, st));
     if (set_state_from_stage(p, st, tn, !keep_dn)) return -1;

@@ -250,18 +250,21 @@ def holders_sum(halo, me, own, recv):
 
 
 def dist_exchange(send):
-    """Neighbour exchange of device tensors over the default torch.distributed group (NCCL)."""
+    """Neighbour exchange of device tensors over the default torch.distributed group (NCCL; with a gloo group — ranks
+    sharing a GPU in the tests — the set-up messages pass through host memory)."""
     import torch
     import torch.distributed as dist
-    recv = {nb: torch.empty_like(t) for nb, t in send.items()}
+    via_host = dist.get_backend() == "gloo"
+    out = {nb: (t.cpu().contiguous() if via_host else t) for nb, t in send.items()}
+    recv = {nb: torch.empty_like(t) for nb, t in out.items()}
     ops = []
-    for nb in sorted(send):
-        ops.append(dist.P2POp(dist.isend, send[nb], nb))
+    for nb in sorted(out):
+        ops.append(dist.P2POp(dist.isend, out[nb], nb))
         ops.append(dist.P2POp(dist.irecv, recv[nb], nb))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    return recv
+    return {nb: t.to(send[nb].device) for nb, t in recv.items()} if via_host else recv
 
 
 def gather_node_lists(local_nodes, size):
@@ -270,11 +273,12 @@ def gather_node_lists(local_nodes, size):
     import torch.distributed as dist
     if size == 1:
         return [local_nodes.cpu().numpy()]
-    n = torch.tensor([local_nodes.numel()], device=local_nodes.device)
+    dev = torch.device("cpu") if dist.get_backend() == "gloo" else local_nodes.device
+    n = torch.tensor([local_nodes.numel()], device=dev)
     sizes = [torch.zeros_like(n) for _ in range(size)]
     dist.all_gather(sizes, n)
     mx = int(max(int(s) for s in sizes))
-    buf = torch.zeros(mx, dtype=torch.int64, device=local_nodes.device)
+    buf = torch.zeros(mx, dtype=torch.int64, device=dev)
     buf[:local_nodes.numel()] = local_nodes
     out = [torch.empty_like(buf) for _ in range(size)]
     dist.all_gather(out, buf)
@@ -416,7 +420,7 @@ def finish_rank(loc, alpha=DAMP_DEFAULT, keep_csr=False):
         lists = gather_node_lists(loc["local_nodes"], size)
         halo = maps.halo_plan(rank, size, lists)
         recv = dist_exchange(holders_send(halo, shared_partials(loc, halo)))
-        t = torch.tensor([dt], dtype=torch.float64, device=loc["m_node"].device)
+        t = torch.tensor([dt], dtype=torch.float64, device="cpu" if dist.get_backend() == "gloo" else loc["m_node"].device)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)                                               # Data_prepare.py:151-154
         dt = float(t.item())
     out = structured_rank_plan(loc, halo, recv, dt, alpha, keep_csr)

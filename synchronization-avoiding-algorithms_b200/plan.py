@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -61,6 +62,9 @@ ABI = {
     "saa_plan_stream": (_vp, [_vp]),
     "saa_step_host": (_int, [_vp, _vp, _vp, _f64, _int, _vp]),
     "saa_step_host_ex": (_int, [_vp, _vp, _vp, _f64, _int, _vp, _int]),
+    "saa_plan_host_pipe_info": (_int, [_vp, _int, _vp, _vp, _vp, _int]),
+    "saa_host_alloc": (_vp, [_i64]),
+    "saa_host_free": (_int, [_vp]),
     "saa_plan_set_history": (_int, [_vp, _vp, _i64, _i64, _i64]),
     "saa_plan_history_count": (_i64, [_vp]),
     "saa_plan_read_history": (_int, [_vp, _i64, _i64, _vp]),
@@ -84,6 +88,28 @@ ABI = {
 
 class SaaError(RuntimeError):
     pass
+
+
+PINNED_POOL = 4
+
+
+class _PinnedVector:
+    """n float64 of page-locked host memory (saa_host_alloc); numpy arrays made from it keep it alive through
+    their .base and it returns the memory when the last one is gone."""
+
+    def __init__(self, n):
+        self.ptr = lib().saa_host_alloc(8 * int(n))
+        if not self.ptr:
+            raise SaaError("saa_host_alloc: " + lib().saa_last_error().decode())
+        self.__array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().saa_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 def library_path():
@@ -302,6 +328,32 @@ class StepPlan:
     def matfree_bytes(self):
         return int(lib().saa_plan_matfree_bytes(self.h))
 
+    def _host_out(self):
+        """The array a host call returns d1 in.  From 1 MiB per vector on it is a view of page-locked memory
+        (saa_host_alloc), so that this download and — once the caller has rotated it into d_0 / d_n
+        (Data_prepare.py:233-234) — the next uploads are asynchronous full-rate PCIe copies that the pipelined call
+        can overlap.  A buffer is handed out again only when no array refers to it any more (the views hold a
+        reference to their owner); at most PINNED_POOL buffers exist per plan, beyond that (a caller that keeps every
+        d1) plain numpy memory is returned.  SAA_STEP_HOST_PINNED=0 switches it off."""
+        n = self.n_dof
+        if 8 * n < (1 << 20) or os.environ.get("SAA_STEP_HOST_PINNED", "1") == "0":
+            return np.empty(n)
+        pool = self.__dict__.setdefault("_pinned_pool", [])
+        for i in range(len(pool)):
+            if sys.getrefcount(pool[i]) == 2:            # the list's reference + getrefcount's argument: no array left
+                return np.asarray(pool[i])
+        if len(pool) < PINNED_POOL:
+            pool.append(_PinnedVector(n))
+            return np.asarray(pool[-1])
+        return np.empty(n)
+
+    def host_pipe_info(self, mode=MODE_LOCAL):
+        """(K, slice_end[K], need_upload[K]) of the pipelined host call for `mode`; K = 0: plain sequence."""
+        k = ctypes.c_int(0)
+        se, nu = np.zeros(64, dtype=np.int64), np.zeros(64, dtype=np.int32)
+        _check(lib().saa_plan_host_pipe_info(self.h, int(mode), ctypes.byref(k), _p(se), _p(nu), 64), "saa_plan_host_pipe_info")
+        return k.value, se[:k.value].copy(), nu[:k.value].copy()
+
     def step_host(self, d0, dn, tn, mode=MODE_LOCAL, out=None):
         """One parallel_explicit_solver_dis_pre evaluation with host buffers -> d1 (n_dof,).
 
@@ -315,7 +367,7 @@ class StepPlan:
         dn = np.ascontiguousarray(dn, dtype=np.float64).reshape(-1)
         if d0.size != self.n_dof or dn.size != self.n_dof:
             raise SaaError("step_host: wrong vector length")
-        d1 = np.empty(self.n_dof) if out is None else out
+        d1 = self._host_out() if out is None else out
         prev = getattr(self, "_host_prev_d0", None)
         flags = 0
         if prev is not None and prev.ctypes.data == dn.ctypes.data and not os.environ.get("SAA_STEP_HOST_FULL_UPLOAD"):

@@ -282,6 +282,14 @@ def test_fused_peer_step_two_processes_sharing_this_gpu():
     _run_workers("peer", "beam_coarse_P2", 2, timeout=420)
 
 
+def test_mid_size_partition_two_processes_sharing_this_gpu():
+    """Same on the 29 025-DOF METIS case (several boundary slices and shared-row units per rank), including the
+    pipelined synchronised host call (saa_step_host_ex, MODE_SYNC) against the plain one and the resident steps."""
+    if not _have_mid(2):
+        pytest.skip("mid-size fixture not generated")
+    _run_workers("peer", "mid_np2", 2, timeout=420)
+
+
 def test_mid_fixture_is_reproducible():
     """tests/golden/mid_np*.npz were produced on another B200 box by oracle/gen_golden_mid.py (device assembly -> CPU
     oracle).  Regenerating them here must give the same bits (deterministic device assembly, same METIS partition), and
@@ -498,3 +506,106 @@ def test_mass_stream_per_node_or_per_dof_same_bits(monkeypatch):
         o.run(40, model=True)
         for k in range(3):
             assert bits_equal(plans[k].d0(), o.d0(k)), (variant, "local", k)
+
+
+def _host_loop(pl, d0, dn, tn, dt, n, mode=splan.MODE_LOCAL):
+    """the rotation of Data_prepare.py:223-235 with host arrays"""
+    d_0, d_n = d0.copy(), dn.copy()
+    for _ in range(n):
+        d1 = pl.step_host(d_0, d_n, tn, mode)
+        d_n = d_0
+        d_0 = d1
+        tn = tn + dt
+    return d_0, d_n, tn
+
+
+@pytest.mark.parametrize("chunks", [2, 5, 13])
+@pytest.mark.parametrize("name,q", [("struct_m6_P3", 1), ("struct_m4_P2", 0), ("beam_coarse_P1", 0)])
+def test_pipelined_host_call_equals_plain_call_and_oracle(name, q, chunks, monkeypatch):
+    """saa_step_host_ex cut into `chunks` pieces of caller-order rows (upload / step / download overlapped on three
+    streams; SAA_STEP_HOST_PIPELINE forces the chunking that plans of >= 4 MiB per vector get by default) returns the
+    bits of the plain upload-step-download sequence and of the oracle: rotated loop (dn not uploaded), fresh arrays
+    (both uploaded), tn > 1."""
+    g = load_golden(name)
+    r = g["ranks"][q]
+    n = r["F"].size
+    fo = oracle_module()
+    rng = np.random.default_rng(11)
+    d0, dn = rng.standard_normal(n) * 1e-3, rng.standard_normal(n) * 1e-3
+    monkeypatch.setenv("SAA_STEP_HOST_PIPELINE", str(chunks))
+    pl = golden_plans_single(g, q)
+    a0, an, atn = _host_loop(pl, d0, dn, 0.4, float(g["dt"]), 12)
+    K, slice_end, need = pl.host_pipe_info(splan.MODE_LOCAL)
+    assert K == min(chunks, n // 3) and slice_end[-1] > 0 and (np.diff(slice_end) >= 0).all() and (np.diff(need) >= 0).all()
+    assert pl.host_uploads_skipped == 11
+    got_fresh = pl.step_host(d0, dn, 1.7, splan.MODE_LOCAL)          # not the rotated array: both vectors cross
+    monkeypatch.setenv("SAA_STEP_HOST_PIPELINE", "0")
+    pl2 = golden_plans_single(g, q)
+    b0, bn, btn = _host_loop(pl2, d0, dn, 0.4, float(g["dt"]), 12)
+    assert pl2.host_pipe_info(splan.MODE_LOCAL)[0] == 0
+    assert bits_equal(a0, b0) and bits_equal(an, bn) and atn == btn
+    assert bits_equal(got_fresh, pl2.step_host(d0, dn, 1.7, splan.MODE_LOCAL))
+    o = fo.OracleProblem(len(g["points"]), [r], g["dt"], float(g["alpha"]))
+    o.set_state(0, d0, dn, 0.4)
+    o.run(12, model=True)
+    assert bits_equal(a0, o.d0(0))
+    o.close()
+    # the plan's resident state after a pipelined call is (d1, d0, tn + dt), like after the plain one
+    c0, cn, ctn = pl.get_state()
+    e0, en, etn = pl2.get_state()
+    assert bits_equal(c0, e0) and bits_equal(cn, en) and ctn == etn
+
+
+def test_pipelined_host_call_on_a_morton_ordered_plan(monkeypatch):
+    """Device set-up with the rows laid out along a Morton curve: the chunks' column windows overlap irregularly
+    (need_upload runs ahead of the chunk index); still every row exactly once, same bits as the plain sequence and
+    as the device-resident steps."""
+    from saa_b200 import device_setup
+    pts, cells, fac = mesh.structured_beam(5, length=6)
+    monkeypatch.setenv("SAA_STEP_HOST_PIPELINE", "7")
+    pl, info = device_setup.build_mesh_rank(pts, cells, fac, np.zeros(len(cells), dtype=np.int64), 0, 1)
+    n = pl.n_dof
+    a0, an, atn = _host_loop(pl, np.zeros(n), np.zeros(n), 0.0, info["dt"], 25)
+    K, slice_end, need = pl.host_pipe_info(splan.MODE_LOCAL)
+    assert K == 7 and need[-1] == 6
+    monkeypatch.setenv("SAA_STEP_HOST_PIPELINE", "0")
+    b0, bn, btn = _host_loop(pl, np.zeros(n), np.zeros(n), 0.0, info["dt"], 25)
+    assert bits_equal(a0, b0) and bits_equal(an, bn) and atn == btn and np.abs(a0).max() > 0
+    z = np.zeros(n)
+    pl.set_state(z, z, 0.0)
+    pl.step(25, splan.MODE_LOCAL)
+    pl.synchronize()
+    assert bits_equal(pl.d0(), a0)
+
+
+def test_host_call_returns_page_locked_arrays_from_a_small_pool(monkeypatch):
+    """From 1 MiB per vector on step_host hands d1 out as a view of page-locked memory; a buffer is reused only when
+    no array refers to it any more, so the three arrays of the reference's rotation cycle through <= 4 buffers and a
+    caller that keeps every d1 is never overwritten (it gets plain numpy memory beyond the pool)."""
+    from saa_b200 import device_setup
+    pts, cells, fac = mesh.structured_beam(16, length=10)
+    pl, info = device_setup.build_mesh_rank(pts, cells, fac, np.zeros(len(cells), dtype=np.int64), 0, 1)
+    n = pl.n_dof
+    assert 8 * n >= (1 << 20)
+    d_0, d_n, tn = np.zeros(n), np.zeros(n), 0.0
+    seen = set()
+    for _ in range(12):
+        d1 = pl.step_host(d_0, d_n, tn, splan.MODE_LOCAL)
+        seen.add(d1.ctypes.data)
+        d_n, d_0, tn = d_0, d1, tn + info["dt"]
+    assert len(seen) <= splan.PINNED_POOL and len(pl._pinned_pool) <= splan.PINNED_POOL
+    assert pl.host_uploads_skipped >= 11
+    z = np.zeros(n)
+    pl.set_state(z, z, 0.0)
+    pl.step(12, splan.MODE_LOCAL)
+    pl.synchronize()
+    assert bits_equal(pl.d0(), d_0)
+    kept = [d_0.copy()]
+    keep = []
+    for _ in range(8):                                           # a caller that keeps every result
+        d1 = pl.step_host(d_0, d_n, tn, splan.MODE_LOCAL)
+        keep.append(d1)
+        kept.append(d1.copy())
+        d_n, d_0, tn = d_0, d1, tn + info["dt"]
+    assert all(bits_equal(a, b) for a, b in zip(keep, kept[1:]))
+    assert len({a.ctypes.data for a in keep}) == 8

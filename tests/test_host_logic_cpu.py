@@ -151,3 +151,44 @@ def test_compat_stand_ins_step_aside_for_real_packages(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-2000:]
     assert "x.hdf5.npz" in r.stderr and "not installed" in r.stderr
+
+
+@pytest.mark.parametrize("m,size,grid", [(4, 8, None), (3, 4, None), (5, 2, (1, 2, 1)), (4, 8, (2, 1, 4))])
+def test_block_partition_of_the_structured_beam(m, size, grid):
+    """device_setup.block_partition (host epart of the px x py x pz block grid): whole hexahedra per rank, rank =
+    (bx*py + by)*pz + bz with block b owning hexahedra [b*n//p, (b+1)*n//p) along each axis, element order ascending."""
+    nx, ny, nz = mesh.structured_beam_dims(m)
+    px, py, pz = grid or ds.block_grid(size)
+    assert px * py * pz == size
+    ep = ds.block_partition(m, size, grid=grid)
+    assert ep.shape == (6 * nx * ny * nz,) and set(np.unique(ep)) == set(range(size))
+    hexes = ep.reshape(-1, 6)
+    assert (hexes == hexes[:, :1]).all()                         # the six tetrahedra of a hexahedron stay together
+    H = hexes[:, 0].reshape(nx, ny, nz)
+    for r in range(size):
+        bz, by, bx = r % pz, (r // pz) % py, r // (pz * py)
+        sl = tuple(slice((b * n) // p, ((b + 1) * n) // p) for b, n, p in ((bx, nx, px), (by, ny, py), (bz, nz, pz)))
+        assert (H[sl] == r).all() and (H == r).sum() == np.prod([s.stop - s.start for s in sl])
+    # with P = 8 the partition has edges held by 4 ranks and the beam's centre line held by 8 (ascending-rank sums with >= 3 holders)
+    if (px, py, pz) == (2, 2, 2):
+        pts, cells, _ = mesh.structured_beam(m)
+        holders = np.zeros((len(pts), size), dtype=bool)
+        holders[cells.reshape(-1), np.repeat(ep, 4)] = True
+        assert holders.sum(1).max() == 8 and (holders.sum(1) == 4).any()
+
+
+def test_plan_cache_fingerprints_notice_changed_inputs():
+    """Tools/Dynamic_solver.py caches the device plan per LocalK object; the cache signature covers F_rankwise, l_M and
+    Local_Dirichlet (address, shape, sampled content), so replacing or rescaling one of them cannot leave stale copies."""
+    pkg = os.path.join(ROOT, "synchronization-avoiding-algorithms_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from Tools.Dynamic_solver import _fingerprint
+    F = np.arange(9000, dtype=np.float64).reshape(-1, 1)
+    f0 = _fingerprint(F)
+    assert _fingerprint(F) == f0
+    assert _fingerprint(F.copy()) != f0                          # another array, even with equal content: new address
+    F *= 2.0
+    assert _fingerprint(F) != f0                                 # same array, rescaled in place
+    D = list(range(0, 300, 3))
+    assert _fingerprint(D) == _fingerprint(list(D)) and _fingerprint(D) != _fingerprint(D[:-1]) and _fingerprint(D) != _fingerprint([d + 1 for d in D])
