@@ -180,7 +180,6 @@ struct saa_plan {
         int need_boundary = -1;               // table 1: the boundary slices need the uploads of chunks <= this
     } hp[2];                                  // [0] local steps, [1] synchronised steps of a plan with neighbours
     std::vector<cudaEvent_t> hp_ev_up, hp_ev_cmp;
-    cudaEvent_t hp_ev_final = nullptr;
     cudaStream_t hp_s_in = nullptr, hp_s_out = nullptr;
     double *d_force = nullptr;              // [2 * n_rows] scratch of the stand-alone force synchronisation
     // matrix-free mode (K5, saa_plan_set_matfree_dev)
@@ -592,7 +591,6 @@ extern "C" int saa_plan_destroy(saa_plan *p)
         if (p->ev_msg) cudaEventDestroy(p->ev_msg);
         for (cudaEvent_t e : p->hp_ev_up) cudaEventDestroy(e);
         for (cudaEvent_t e : p->hp_ev_cmp) cudaEventDestroy(e);
-        if (p->hp_ev_final) cudaEventDestroy(p->hp_ev_final);
         if (p->hp_s_in) cudaStreamDestroy(p->hp_s_in);
         if (p->hp_s_out) cudaStreamDestroy(p->hp_s_out);
         if (p->stream) cudaStreamDestroy(p->stream);
@@ -1307,7 +1305,6 @@ static int host_pipe_build(saa_plan *p, int table)
     if (!p->hp_s_in) {
         CK(cudaStreamCreateWithFlags(&p->hp_s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&p->hp_s_out, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&p->hp_ev_final, cudaEventDisableTiming));
     }
     while ((int)p->hp_ev_up.size() < K) {
         cudaEvent_t a, b;
@@ -1332,52 +1329,54 @@ static int host_pipe_step(saa_plan *p, int table, const double *d0, const double
     CK(cudaMemcpyAsync(&p->d_clk[p->cur].tn, &tn, sizeof(double), cudaMemcpyHostToDevice, s_in));
     double *b0 = p->d_buf[p->cur], *b1 = p->d_buf[p->cur ^ 1];
     double *stage_dn = p->d_stage + p->n_dof, *stage_out = p->d_stage + 2 * p->n_dof;
-    for (int c = 0; c < K; ++c) {                                // stage 1: uploads, in order
+    // stage 1: the copies of all chunks back to back on s_in (nothing but copies on the copy streams: a kernel between
+    // two copies of a stream leaves the PCIe link idle for the kernel and two dependency hand-overs)
+    for (int c = 0; c < K; ++c) {
         const int64_t off = h.row_off[c], cnt = h.row_off[c + 1] - off;
         CK(cudaMemcpyAsync(p->d_stage + off, d0 + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s_in));
-        saa_k_scatter_to_internal<<<nblk(cnt, 256), 256, 0, s_in>>>(cnt, p->d_iperm + off, p->d_stage + off, b0);
-        p->launches++;
-        if (!keep_dn) {
-            CK(cudaMemcpyAsync(stage_dn + off, dn + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s_in));
-            saa_k_scatter_to_internal<<<nblk(cnt, 256), 256, 0, s_in>>>(cnt, p->d_iperm + off, stage_dn + off, b1);
-            p->launches++;
-        }
+        if (!keep_dn) CK(cudaMemcpyAsync(stage_dn + off, dn + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s_in));
         CK(cudaEventRecord(p->hp_ev_up[c], s_in));
     }
-    auto download = [&](int c) -> int {                          // stage 3: d1 of the chunk's rows -> external order -> host
+    // stage 2 on the plan's stream: caller order -> internal order of the chunks as they arrive, the step slice range by
+    // slice range, internal -> caller order of the finished rows;  stage 3: their copies back to back on s_out
+    int arrived = -1;
+    auto take_uploads = [&](int upto) -> int {
+        for (int c = arrived + 1; c <= upto; ++c) {
+            const int64_t off = h.row_off[c], cnt = h.row_off[c + 1] - off;
+            CK(cudaStreamWaitEvent(st, p->hp_ev_up[c], 0));
+            saa_k_scatter_to_internal<<<nblk(cnt, 256), 256, 0, st>>>(cnt, p->d_iperm + off, p->d_stage + off, b0);
+            if (!keep_dn) saa_k_scatter_to_internal<<<nblk(cnt, 256), 256, 0, st>>>(cnt, p->d_iperm + off, stage_dn + off, b1);
+            p->launches += keep_dn ? 1 : 2;
+        }
+        arrived = std::max(arrived, upto);
+        return 0;
+    };
+    auto download = [&](int c) -> int {
         const int64_t off = h.row_off[c], cnt = h.row_off[c + 1] - off;
-        saa_k_gather_to_external<<<nblk(cnt, 256), 256, 0, s_out>>>(cnt, p->d_iperm + off, b1, stage_out + off);
+        saa_k_gather_to_external<<<nblk(cnt, 256), 256, 0, st>>>(cnt, p->d_iperm + off, b1, stage_out + off);
         p->launches++;
+        CK(cudaEventRecord(p->hp_ev_cmp[c], st));
+        CK(cudaStreamWaitEvent(s_out, p->hp_ev_cmp[c], 0));
         CK(cudaMemcpyAsync(d1 + off, stage_out + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
         return 0;
     };
-    int waited = -1;
-    auto wait_uploads = [&](int c) -> int {
-        if (c > waited) { CK(cudaStreamWaitEvent(st, p->hp_ev_up[c], 0)); waited = c; }
-        return 0;
-    };
     bool boundary_done = !(sync && p->sh_slices > 0);
-    for (int c = 0; c < K; ++c) {                                // stage 2: the step, slice range by slice range
+    for (int c = 0; c < K; ++c) {
         if (!boundary_done && (h.need_upload[c] >= h.need_boundary || c == K - 1)) {
-            if (wait_uploads(h.need_boundary)) return -1;
+            if (take_uploads(h.need_boundary)) return -1;
             sync_phase_boundary(p, st);                          // K2: partial forces of the shared rows -> neighbours
             if (!use_peer(p) && nccl_exchange(p, st)) return -1;
             boundary_done = true;
         }
-        if (wait_uploads(h.need_upload[c])) return -1;
+        if (take_uploads(h.need_upload[c])) return -1;
         const int64_t s0 = c ? h.slice_end[c - 1] : h.first_slice, s1 = h.slice_end[c];
         if (s1 > s0) launch_interior(p, st, s0, count_sync, c == 0, s1);
         else if (c == 0) launch_interior(p, st, p->n_slices, count_sync, true, p->n_slices);   // no slice, the clock only
-        CK(cudaEventRecord(p->hp_ev_cmp[c], st));
-        if (!(sync && h.has_shared[c])) {
-            CK(cudaStreamWaitEvent(s_out, p->hp_ev_cmp[c], 0));
-            if (download(c)) return -1;
-        }
+        if (!(sync && h.has_shared[c]) && download(c)) return -1;
     }
+    if (take_uploads(K - 1)) return -1;                          // the whole state is resident afterwards, whatever the step read
     if (sync) {
         sync_phase_shared(p, st);                                // K3: rank-ordered sums + update of the shared rows; swaps the levels
-        CK(cudaEventRecord(p->hp_ev_final, st));
-        CK(cudaStreamWaitEvent(s_out, p->hp_ev_final, 0));
         for (int c = 0; c < K; ++c)
             if (h.has_shared[c] && download(c)) return -1;
     } else {
