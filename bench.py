@@ -314,6 +314,48 @@ def time_repeats(pl, torch, stream, steps, mode, launch, barrier, max_over_ranks
     return out, launches
 
 
+def time_host_calls(pl, torch, dist, world, mode, dt, e2e_steps, barrier, max_over_ranks, n_dof_global):
+    """The loop of Data_prepare.py:223-235 with host arrays through StepPlan.step_host (saa_step_host_ex): d1 comes back
+    in page-locked memory owned by the plan's pool and is rotated into d_0 / d_n, so from the second call on every vector
+    that crosses PCIe is pinned.  The call is synchronous: wall clock covers copies + kernels.  Afterwards the result is
+    compared bit for bit with the same number of device-resident steps from the same state."""
+    from saa_b200 import plan as splan  # noqa: F401
+    n_dof_local = pl.n_dof
+    s0, sn, tn0 = pl.get_state()
+    h0, hn, tn = s0, sn, tn0
+    for _ in range(3):
+        h1 = pl.step_host(h0, hn, tn, mode)
+        hn, h0 = h0, h1
+        tn = tn + dt
+    barrier()
+    skipped0 = getattr(pl, "host_uploads_skipped", 0)
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h1 = pl.step_host(h0, hn, tn, mode)          # d1 lands in host memory every call
+        hn, h0 = h0, h1                              # d_n = d_0; d_0 = d1 (Data_prepare.py:233-234)
+        tn = tn + dt
+    pl.synchronize()
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - w0) * 1e3)
+    dn_skipped = getattr(pl, "host_uploads_skipped", 0) - skipped0
+    h2d = (8 * n_dof_local * (2 * e2e_steps - dn_skipped)) / e2e_steps
+    pipe_k, _, pipe_need = pl.host_pipe_info(mode)
+    pipe = {"chunks": int(pipe_k), "max_lag_chunks": int(max(pipe_need - np.arange(pipe_k))) if pipe_k else None,
+            "pinned_result_buffers": len(getattr(pl, "_pinned_pool", []))}
+    pl.set_state(s0, sn, tn0)
+    pl.step(3 + e2e_steps, mode)
+    pl.synchronize()
+    same = bool(np.array_equal(pl.d0().view(np.uint64), h0.view(np.uint64)))
+    if world > 1:
+        tt = torch.tensor([1.0 if same else 0.0], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        same = bool(tt.item() == 1.0)
+    return {"value": n_dof_global * e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * n_dof_local,
+            "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "dn_uploads_skipped": dn_skipped,
+            "pipeline": pipe, "bit_identical_to_resident_steps": same}
+
+
 def bits_equal_dev(torch, a, b):
     return bool(torch.equal(a.view(torch.int64), b.view(torch.int64)))
 
@@ -661,39 +703,7 @@ def main():
         ms_local = float(np.median(rl)) / steps
 
     # ---- end to end through the reference-facing host call -----------------------------------------
-    # the loop of Data_prepare.py:223-235 with host arrays: d1 comes back in page-locked memory owned by the plan's pool
-    # and is rotated into d_0 / d_n, so from the second call on every vector that crosses PCIe is pinned
-    s0, sn, tn0 = pl.get_state()
-    h0, hn, tn = s0, sn, tn0
-    for _ in range(3):
-        h1 = pl.step_host(h0, hn, tn, mode)
-        hn, h0 = h0, h1
-        tn = tn + dtv
-    barrier()
-    skipped0 = getattr(pl, "host_uploads_skipped", 0)
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        h1 = pl.step_host(h0, hn, tn, mode)          # d1 lands in host memory every call
-        hn, h0 = h0, h1                              # d_n = d_0; d_0 = d1 (Data_prepare.py:233-234)
-        tn = tn + dtv
-    pl.synchronize()
-    barrier()
-    ms_e2e = max_over_ranks((time.perf_counter() - w0) * 1e3)   # the call is synchronous: wall clock covers copies + kernels
-    dn_skipped = getattr(pl, "host_uploads_skipped", 0) - skipped0
-    h2d = (8 * n_dof_local * (2 * e2e_steps - dn_skipped)) / e2e_steps
-    pipe_k, _, pipe_need = pl.host_pipe_info(mode)
-    pipe = {"chunks": int(pipe_k), "max_lag_chunks": int(max(pipe_need - np.arange(pipe_k))) if pipe_k else None,
-            "pinned_result_buffers": len(getattr(pl, "_pinned_pool", []))}
-    # the host-call results against the device-resident steps from the same state: bit for bit
-    pl.set_state(s0, sn, tn0)
-    pl.step(3 + e2e_steps, mode)
-    pl.synchronize()
-    e2e_same = bool(np.array_equal(pl.d0().view(np.uint64), h0.view(np.uint64)))
-    if world > 1:
-        tt = torch.tensor([1.0 if e2e_same else 0.0], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
-        e2e_same = bool(tt.item() == 1.0)
-    del h0, hn, h1, s0, sn
+    e2e = time_host_calls(pl, torch, dist, world, mode, dtv, e2e_steps, barrier, max_over_ranks, n_dof_global)
     clocks = sampler.stop() if sampler else None
 
     # ---- cross-path check on the timed mesh (N > 1, peer transport) ----------------------------------
@@ -742,10 +752,11 @@ def main():
                 r2, _ = time_repeats(pl2, torch, st2, k2, md2, launch, barrier, max_over_ranks, 5, 200.0, 10)
                 ms2 = float(np.median(r2))
                 b2 = max_over_ranks(float(pl2.matrix_bytes + pl2.vector_bytes))
+                e2 = time_host_calls(pl2, torch, dist, w2, md2, info2["dt"], 200 if m2 <= 32 else 60, barrier, max_over_ranks, 3 * info2["n_nodes"])
                 also.append({"workload": workload_name(m2, 3 * info2["n_nodes"], info2["n_elem"]), "n_gpus": w2, "steps": k2, "repeats": len(r2),
                              "value": 3 * info2["n_nodes"] * k2 / (ms2 * 1e-3), "ms_per_step": ms2 / k2,
                              "ms_per_step_min": min(r2) / k2, "ms_per_step_max": max(r2) / k2,
-                             "roofline_frac": b2 / (ms2 / k2 * 1e-3) / 1e9 / peak, "nnz_per_row": pl2.nnz / pl2.n_dof})
+                             "roofline_frac": b2 / (ms2 / k2 * 1e-3) / 1e9 / peak, "nnz_per_row": pl2.nnz / pl2.n_dof, "e2e": e2})
                 pl2.close()
                 del pl2
                 torch.cuda.empty_cache()
@@ -775,13 +786,9 @@ def main():
                        "nnz_per_row": nnz / n_dof_local, "local_dof_rank0": n_dof_local,
                        "launch": args.launch, "dt": dtv, "setup_s": round(t_setup, 1), "ms_per_step_without_exchange": ms_local,
                        "l2": "inputs larger than L2: matrix stream per step per GPU = %.0f MB vs 126 MB L2" % mat_mb},
-            "e2e": {"value": n_dof_global * e2e_steps / (ms_e2e * 1e-3), "unit": "DOF-steps/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * n_dof_local,
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "dn_uploads_skipped": dn_skipped,
-                    "pipeline": pipe, "bit_identical_to_resident_steps": e2e_same,
-                    "call": "saa_step_host_ex (one parallel_explicit_solver_dis_pre evaluation per call, host d0/dn in, d1 out in page-locked "
-                            "memory that the caller rotates into d0/dn; dn = the previous call's d0 array is recognised and not uploaded "
-                            "again; upload, step and download of the row chunks overlap on three streams)"},
+            "e2e": dict(e2e, call="saa_step_host_ex (one parallel_explicit_solver_dis_pre evaluation per call, host d0/dn in, d1 out in page-locked "
+                                   "memory that the caller rotates into d0/dn; dn = the previous call's d0 array is recognised and not uploaded "
+                                   "again; upload, step and download of the row chunks overlap on three streams)"),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

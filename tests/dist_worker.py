@@ -85,6 +85,20 @@ if mode == "host":
                 acc = acc + got[off[kk] + 3 * slot: off[kk] + 3 * slot + 3]
         out[pos] = acc
     assert bits_equal(out, want)
+    # the set-up exchanges of the device path (device_setup.gather_node_lists / dist_exchange / holders_sum) over a gloo
+    # group pass through host memory: rank-ordered sums of per-node partials (lumped mass, load) at the shared nodes
+    import torch
+    from saa_b200 import device_setup as ds
+    lists2 = ds.gather_node_lists(torch.as_tensor(np.asarray(nodes, dtype=np.int64)), size)
+    assert len(lists2) == size and all(np.array_equal(a, b) for a, b in zip(lists2, lists))
+    part = rng.standard_normal((len(nodes), 2)) * 10.0 ** rng.integers(-3, 3, (len(nodes), 2))
+    own_t = torch.as_tensor(part)[torch.as_tensor(np.asarray(hp["shared_pos"], dtype=np.int64))]
+    tot = ds.holders_sum(hp, rank, own_t, ds.dist_exchange(ds.holders_send(hp, own_t)))
+    allp = comm.bcast(comm.gather(part, root=0), root=0)
+    glob = np.zeros((len(Points), 2))
+    for r in range(size):
+        glob[np.asarray(lists[r], dtype=np.int64)] += allp[r]
+    assert bits_equal(tot.numpy(), glob[np.asarray(nodes, dtype=np.int64)[np.asarray(hp["shared_pos"], dtype=np.int64)]])
 else:
     got = DT.syn_cpus(size, rank, f.reshape(-1, 1), len(Points), nodes)
     assert got.shape == (f.size, 1) and bits_equal(got, want)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import saa_b200  # noqa: F401
-from saa_b200 import comm, device_setup as ds, maps, mesh
+from saa_b200 import comm, device_setup as ds, maps, mesh, plan as splan
 from util import ROOT
 
 PKG = os.path.join(ROOT, "synchronization-avoiding-algorithms_b200")
@@ -192,3 +192,56 @@ def test_plan_cache_fingerprints_notice_changed_inputs():
     assert _fingerprint(F) != f0                                 # same array, rescaled in place
     D = list(range(0, 300, 3))
     assert _fingerprint(D) == _fingerprint(list(D)) and _fingerprint(D) != _fingerprint(D[:-1]) and _fingerprint(D) != _fingerprint([d + 1 for d in D])
+
+
+def test_host_result_pool_policy(monkeypatch):
+    """StepPlan._host_out (the array step_host returns d1 in): small plans get plain numpy memory; from 1 MiB per vector
+    on, views of <= PINNED_POOL page-locked buffers, a buffer being reused only when no array — views and views of views
+    included — refers to it any more; a caller that keeps every result falls back to plain memory beyond the pool.
+    Page-locked memory needs the CUDA driver, so the allocation itself is replaced by ordinary memory here."""
+    import ctypes
+
+    class FakePinned:
+        made = 0
+
+        def __init__(self, n):
+            FakePinned.made += 1
+            self.buf = (ctypes.c_double * int(n))()
+            self.__array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (ctypes.addressof(self.buf), False), "version": 3}
+
+    monkeypatch.setattr(splan, "_PinnedVector", FakePinned)
+    small = splan.StepPlan.__new__(splan.StepPlan)
+    small.n_dof, small.h = 300, None
+    a = small._host_out()
+    assert a.shape == (300,) and a.base is None and FakePinned.made == 0
+    pl = splan.StepPlan.__new__(splan.StepPlan)
+    pl.n_dof, pl.h = 1 << 17, None
+    # the reference's rotation: d_n, d_0 and the new d1 are alive at any time (+ the plan keeps the previous d0)
+    d_n, d_0, seen = np.zeros(pl.n_dof), np.zeros(pl.n_dof), set()
+    for i in range(20):
+        d1 = pl._host_out()
+        assert d1.flags.writeable and d1.dtype == np.float64 and d1.shape == (pl.n_dof,)
+        assert d1.ctypes.data not in (d_0.ctypes.data, d_n.ctypes.data)         # never a buffer still in use
+        d1[:] = i
+        seen.add(d1.ctypes.data)
+        pl._host_prev_d0 = d_0
+        d_n, d_0 = d_0, d1.reshape(-1, 1)                                        # the shim returns (3n,1) views
+        assert d_n.reshape(-1)[0] == max(i - 1, 0) and d_0[0, 0] == i
+    assert len(seen) <= splan.PINNED_POOL and FakePinned.made == len(pl._pinned_pool) <= splan.PINNED_POOL
+    # a slice of a view keeps its buffer busy
+    tail = d_0[5:9]
+    del d_0, d_n, d1
+    pl._host_prev_d0 = None
+    busy = tail.ctypes.data
+    for _ in range(6):
+        x = pl._host_out()
+        assert not (x.ctypes.data <= busy < x.ctypes.data + 8 * pl.n_dof)
+    # a caller that keeps everything: the pool is exhausted, plain memory from then on, nothing is overwritten
+    keep = [pl._host_out() for _ in range(splan.PINNED_POOL + 3)]
+    for i, k in enumerate(keep):
+        k[:] = 100 + i
+    assert all(k[0] == 100 + i for i, k in enumerate(keep)) and len({k.ctypes.data for k in keep}) == len(keep)
+    assert sum(k.base is None for k in keep) >= 3 and len(pl._pinned_pool) == splan.PINNED_POOL
+    monkeypatch.setenv("SAA_STEP_HOST_PINNED", "0")
+    del keep
+    assert pl._host_out().base is None
