@@ -1,4 +1,5 @@
 """The explicit time step behind the reference's signature (/root/reference/Tools/Dynamic_solver.py:9-34)."""
+import os
 import weakref
 
 import numpy as np
@@ -24,6 +25,52 @@ def _fingerprint(a):
     return (len(v), int(v[::max(1, v.size // 1024)].sum()) if v.size else 0)
 
 
+def _device_for(rank):
+    """The GPU of this process: SAA_DEVICE if set, else the launcher's local rank (torchrun, Open MPI, MVAPICH, Slurm),
+    else the global rank — modulo the number of visible GPUs (ranks share GPUs when there are more ranks than GPUs)."""
+    n = max(1, _plan.device_count())
+    for var in ("SAA_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"):
+        v = os.environ.get(var)
+        if v is not None and v.lstrip("-").isdigit():
+            return int(v) % n
+    return int(rank) % n
+
+
+def _attach_device_transport(p, c):
+    """Carry the halo messages between the GPUs themselves when the ranks form a torch.distributed group (torchrun with
+    the mpi4py stand-in): NVLink peer-memory stores, the neighbours' receive areas mapped through CUDA IPC — the
+    reference-facing call is then ONE saa_step_host_ex(MODE_SYNC) per step instead of upload + device-to-host messages +
+    a host exchange + download.  Collective; every rank gets the same answer: "peer" or "host" (a real mpi4py
+    communicator, GPUs without peer access, SAA_SHIM_TRANSPORT=host, or a mapping failure on ANY rank -> host messages
+    through the caller's communicator).  Same bits either way (tests/test_tools_shim.py)."""
+    if os.environ.get("SAA_SHIM_TRANSPORT", "auto") == "host" or not hasattr(c, "dist"):
+        return "host", p
+    from saa_b200 import multi
+    dist, why = c.dist, None
+    try:
+        ok = multi.peer_access_everywhere(p)
+    except Exception as e:                                   # no collective is pending on the other ranks after a failure here
+        ok, why = False, e
+    flags = [None] * dist.get_world_size()
+    dist.all_gather_object(flags, bool(ok))
+    if not all(flags):
+        return "host", p
+    exports = [None] * dist.get_world_size()
+    dist.all_gather_object(exports, p.peer_export())
+    try:
+        p.peer_attach(exports)
+        good = True
+    except Exception as e:
+        good, why = False, e
+    dist.all_gather_object(flags, good)
+    if all(flags):
+        return "peer", p
+    if good:                                                 # attached here but not everywhere: this plan would still use its peers
+        return "host", None                                  # -> the caller builds a fresh plan without them
+    print(f"[saa_b200] peer transport not available on rank {p.rank} ({why}); halo messages go through the host", flush=True)
+    return "host", p
+
+
 def _plan_for(LocalK, F_rankwise, Local_nodes, Local_Dirichlet, T, l_M, alpha, size, rank):
     """One device plan per LocalK object: built (and, for size > 1, given its interface description — a
     collective) at the first call, reused while the matrix object, the scalars and the fingerprints of the load,
@@ -44,7 +91,17 @@ def _plan_for(LocalK, F_rankwise, Local_nodes, Local_Dirichlet, T, l_M, alpha, s
         c = _dt.comm
         lists = c.allgather(nodes) if hasattr(c, "allgather") else c.bcast(c.gather(nodes, root=0), root=0)
         halo = _maps.halo_plan(rank, size, lists)
-    p = _plan.StepPlan(LocalK, F_rankwise, l_M, Local_Dirichlet, T.dt, alpha, halo=halo, rank=rank, size=size)
+    dev = _device_for(rank)
+    p = _plan.StepPlan(LocalK, F_rankwise, l_M, Local_Dirichlet, T.dt, alpha, device=dev, halo=halo, rank=rank, size=size)
+    p.shim_transport = "none"
+    if size != 1:
+        p.shim_transport, q = _attach_device_transport(p, _dt.comm)
+        if q is None:
+            p.close()
+            p = _plan.StepPlan(LocalK, F_rankwise, l_M, Local_Dirichlet, T.dt, alpha, device=dev, halo=halo, rank=rank, size=size)
+            p.shim_transport = "host"
+    if os.environ.get("SAA_SHIM_VERBOSE"):
+        print(f"[saa_b200] rank {rank}/{size}: plan of {p.n_dof} DOF on cuda:{dev}, halo transport: {p.shim_transport}", flush=True)
     _plans[key] = (weakref.ref(LocalK), p, sig)
     return p
 
@@ -60,6 +117,8 @@ def parallel_explicit_solver_dis_pre(LocalK, F_rankwise, Points, Local_nodes, Lo
     p = _plan_for(LocalK, F_rankwise, Local_nodes, Local_Dirichlet, T, l_M, alpha, size, rank)
     if MODEL or size == 1:
         d1 = p.step_host(T.d0, T.dn, T.tn, _plan.MODE_LOCAL)
+    elif p.shim_transport == "peer":
+        d1 = p.step_host(T.d0, T.dn, T.tn, _plan.MODE_SYNC)
     else:
         p.set_state(T.d0, T.dn, T.tn)
         p.step_exchange(_dt.comm.exchange)

@@ -245,3 +245,23 @@ def test_host_result_pool_policy(monkeypatch):
     monkeypatch.setenv("SAA_STEP_HOST_PINNED", "0")
     del keep
     assert pl._host_out().base is None
+
+
+def test_shim_picks_the_gpu_of_the_local_rank(monkeypatch):
+    """Tools/Dynamic_solver.py: the plan of a rank lives on GPU (local rank mod visible GPUs); SAA_DEVICE overrides."""
+    pkg = os.path.join(ROOT, "synchronization-avoiding-algorithms_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    import Tools.Dynamic_solver as dsol
+    monkeypatch.setattr(dsol._plan, "device_count", lambda: 4)
+    for var in ("SAA_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"):
+        monkeypatch.delenv(var, raising=False)
+    assert [dsol._device_for(r) for r in range(6)] == [0, 1, 2, 3, 0, 1]
+    monkeypatch.setenv("OMPI_COMM_WORLD_LOCAL_RANK", "2")
+    assert dsol._device_for(7) == 2
+    monkeypatch.setenv("LOCAL_RANK", "5")
+    assert dsol._device_for(7) == 1
+    monkeypatch.setenv("SAA_DEVICE", "3")
+    assert dsol._device_for(0) == 3
+    monkeypatch.setattr(dsol._plan, "device_count", lambda: 0)
+    assert dsol._device_for(9) == 0

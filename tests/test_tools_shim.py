@@ -23,11 +23,11 @@ def _env():
     return e
 
 
-def _torchrun(n, script, *args, timeout=600):
+def _torchrun(n, script, *args, timeout=600, env_extra=None):
     port = 29500 + (os.getpid() * 7 + n) % 500
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), script, *args]
-    r = subprocess.run(cmd, env=_env(), capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run(cmd, env=dict(_env(), **(env_extra or {})), capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
 
@@ -116,17 +116,19 @@ def test_multirank_host_logic_gloo(name, n):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def _run_driver(tmp_path, g, nproc, steps):
+def _run_driver(tmp_path, g, nproc, steps, env_extra=None):
     from saa_b200 import mesh
     vtk = str(tmp_path / "mesh.vtk")
     mesh.write_vtk(vtk, g["points"], g["cells"], g["facets"])
     script = os.path.join(ROOT, "examples", "data_prepare_driver.py")
     args = ["--mesh", vtk, "--steps", str(steps), "--out", str(tmp_path), "--steady"]
+    log = ""
     if nproc == 1:
         r = subprocess.run([sys.executable, script, *args], env=_env(), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     else:
-        _torchrun(nproc, script, *args, timeout=900)
+        log = _torchrun(nproc, script, *args, timeout=900, env_extra=env_extra)
+    _run_driver.log = log
     out = []
     for q in range(nproc):
         path = str(tmp_path / "Results" / "Dynamics" / f"Local-rank-{q}.hdf5")
@@ -152,6 +154,21 @@ def test_data_prepare_shaped_driver_matches_reference_history(tmp_path, name, st
     sh = np.loadtxt(str(tmp_path / "Results" / "Shared_Data" / "Rank=0_shared.csv"), dtype=np.int64, ndmin=1)
     assert np.array_equal(sh, g["ranks"][0]["shared"])
     assert os.path.isfile(str(tmp_path / "Results" / "Static" / "steady_distributed.vtk"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["auto", "host"])
+def test_shim_halo_transport_two_processes(tmp_path, transport):
+    """parallel_explicit_solver_dis_pre with size = 2 under torchrun: by default the shim maps the neighbours' receive
+    areas (CUDA IPC; NVLink stores between GPUs, plain stores when the ranks share a GPU) and every MODEL=False call is one
+    pipelined saa_step_host_ex(MODE_SYNC); SAA_SHIM_TRANSPORT=host keeps the messages on the caller's communicator.  Both
+    reproduce the reference's history bit for bit."""
+    g = load_golden("beam_coarse_P2")
+    H = _run_driver(tmp_path, g, 2, 200, env_extra={"SAA_SHIM_TRANSPORT": transport, "SAA_SHIM_VERBOSE": "1"})
+    assert _run_driver.log.count("halo transport: " + ("peer" if transport == "auto" else "host")) == 2, _run_driver.log[-2000:]
+    for q in range(2):
+        for n in (1, 2, 10, 100):
+            assert bits_equal(H[q][:, n - 1], g[f"hist_{n}_r{q}"]), (transport, n, q)
 
 
 @pytest.mark.gpu
