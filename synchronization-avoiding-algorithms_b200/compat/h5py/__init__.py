@@ -1,11 +1,11 @@
-"""h5py for the reference's result files (Data_prepare.py:243-246, Shared_extraction.py:38-40, Online_predictor.py:321-324).
+"""h5py for the reference's result files (Data_prepare.py:243-246, Shared_extraction.py:32-40, Online_predictor.py:321-324,
+Tools/DNN_tools.py:286-287).
 
-If a real h5py is installed ANYWHERE else on sys.path, this module replaces itself with it at import time — genuine
-HDF5 files are written, whatever the order of PYTHONPATH.  Only when none exists (this image ships no HDF5 library at
-all) the minimal stand-in below is used: `File(path).create_dataset(name, data=...)` / `File(path)[name]` backed by ONE
-`<path>.npz` per file (path "Results/Dynamics/Local-rank-0.hdf5" -> "Results/Dynamics/Local-rank-0.hdf5.npz", dataset
-names = npz keys, `np.load(...)["Displacement"]` reads it).  The substitution is announced once per process on stderr:
-such files cannot be opened by tools that expect HDF5.
+If a real h5py is installed ANYWHERE else on sys.path, this module replaces itself with it at import time, whatever the
+order of PYTHONPATH.  Only when none exists (this image ships no HDF5 library at all) the stand-in below is used: the
+slice of `h5py.File` those scripts need, reading and writing genuine HDF5 through the package's own `hdf5_lite` — the
+files land at exactly the path the caller names and open with h5py / h5dump elsewhere.  (`<path>.npz` archives written by
+earlier versions of this stand-in are still read when `<path>` itself does not exist.)
 """
 import os as _os
 import sys as _sys
@@ -16,45 +16,25 @@ _real = _saa_defer.real("h5py", __file__)
 if _real is not None:
     _sys.modules[__name__] = _real
 else:
-    import numpy as np
+    import importlib.util as _ilu
+
+    import numpy as _np
 
     IS_STAND_IN = True
-    _warned = False
+    _src = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))), "hdf5_lite.py")
+    _spec = _ilu.spec_from_file_location("saa_hdf5_lite", _src)
+    _lite = _ilu.module_from_spec(_spec)
+    _sys.modules["saa_hdf5_lite"] = _lite         # registered before execution (dataclass / annotation lookups by module name)
+    _spec.loader.exec_module(_lite)
 
-    def _warn(path):
-        global _warned
-        if not _warned:
-            _warned = True
-            print(f"[saa_b200.compat.h5py] h5py is not installed: result files are written as NumPy archives, "
-                  f"'{path}' -> '{path}.npz' (same dataset names).  Install h5py to get genuine HDF5.", file=_sys.stderr)
-
-    class File:
-        def __init__(self, name, mode="r"):
-            self.name, self.mode, self._d = str(name), mode, {}
-            if mode.startswith("r"):
-                if _os.path.isfile(self.name) and not _os.path.isfile(self.name + ".npz"):
-                    raise OSError(f"{self.name} exists but h5py is not installed (this stand-in reads only {self.name}.npz)")
-                with np.load(self.name + ".npz") as z:
+    class File(_lite.File):
+        def __init__(self, name, mode="r", **kw):
+            legacy = str(name) + ".npz"
+            if mode == "r" and not _os.path.isfile(str(name)) and _os.path.isfile(legacy):
+                self.filename, self.mode, self._reader, self._addr = str(name), "r", None, {}
+                with _np.load(legacy) as z:
                     self._d = {k: z[k] for k in z.files}
+                return
+            super().__init__(name, mode, **kw)
 
-        def create_dataset(self, name, data=None, compression=None, **_):
-            self._d[name] = np.asarray(data)
-            return self._d[name]
-
-        def __getitem__(self, k):
-            return self._d[k]
-
-        def keys(self):
-            return self._d.keys()
-
-        def close(self):
-            if not self.mode.startswith("r"):
-                _warn(self.name)
-                _os.makedirs(_os.path.dirname(self.name) or ".", exist_ok=True)
-                np.savez_compressed(self.name + ".npz", **self._d)
-
-        def __enter__(self):
-            return self
-
-        def __exit__(self, *a):
-            self.close()
+    Hdf5Error = _lite.Hdf5Error

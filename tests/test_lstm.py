@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import pytest
 
-from util import GOLDEN, ROOT, bits_equal, load_golden, oracle_module
+from util import GOLDEN, ROOT, bits_equal, load_golden, oracle_module, read_result, write_result
 
 PKG = os.path.join(ROOT, "synchronization-avoiding-algorithms_b200")
 if PKG not in sys.path:
@@ -180,7 +180,7 @@ def test_online_predictor_shaped_driver_two_processes(tmp_path):
         for k in range(2):
             hist[k][:, i] = plans[k].d0()
     for k in range(2):
-        got = np.load(str(tmp_path / "Results" / "Dynamics" / f"Modeled_Local-rank-{k}.hdf5.npz"))["Displacement"]
+        got = read_result(tmp_path / "Results" / "Dynamics" / f"Modeled_Local-rank-{k}.hdf5")
         # the K of the driver is assembled by the product (bit-exact only in the authoring container): compare the
         # synchronised warm-up against the golden history loosely and the two execution paths tightly
         assert got.shape == hist[k].shape
@@ -221,13 +221,13 @@ def test_reference_shared_extraction_script_runs_unchanged_on_this_package(tmp_p
         np.savetxt(str(tmp_path / "Results" / "Shared_Data" / f"Rank={q}_shared.csv"), r["shared"], delimiter=",", fmt="%d")
     r0 = g["ranks"][0]
     D = np.stack([g["hist_1_r0"], g["hist_10_r0"], g["hist_100_r0"]], axis=1)
-    np.savez_compressed(str(tmp_path / "Results" / "Dynamics" / "Local-rank-0.hdf5.npz"), Displacement=D)
+    write_result(tmp_path / "Results" / "Dynamics" / "Local-rank-0.hdf5", D)
     env = dict(os.environ)
     env.pop("PYTHONPATH", None)
     r = subprocess.run([sys.executable, os.path.join(PKG, "run_driver.py"), "/root/reference/Shared_extraction.py"], cwd=str(tmp_path),
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    out = np.load(str(tmp_path / "Results" / "sol_on_shared" / "rank=0-shared_dof.hdf5.npz"))["Displacement"]
+    out = read_result(tmp_path / "Results" / "sol_on_shared" / "rank=0-shared_dof.hdf5")
     assert np.array_equal(out, D[r0["loc_dof_shared"], :])
 
 
@@ -388,12 +388,12 @@ def test_pipeline_with_surrogates_trained_by_the_unmodified_reference_script(tmp
     os.makedirs(tmp_path / "Results" / "sol_on_shared", exist_ok=True)
     sync = []
     for q in range(2):
-        D = np.load(str(tmp_path / "Results" / "Dynamics" / f"Local-rank-{q}.hdf5.npz"))["Displacement"]
+        D = read_result(tmp_path / "Results" / "Dynamics" / f"Local-rank-{q}.hdf5")
         sync.append(D)
         sh = np.loadtxt(str(tmp_path / "Results" / "Shared_Data" / f"Rank={q}_shared.csv"), dtype=np.int64, ndmin=1)
         assert np.array_equal(sh, g["ranks"][q]["shared"])                      # same partition as the one the surrogates were trained on
-        np.savez_compressed(str(tmp_path / "Results" / "sol_on_shared" / f"rank={q}-shared_dof.hdf5.npz"),
-                            Displacement=D[g["ranks"][q]["loc_dof_shared"], :])   # Shared_extraction.py:27-40
+        write_result(tmp_path / "Results" / "sol_on_shared" / f"rank={q}-shared_dof.hdf5",
+                     D[g["ranks"][q]["loc_dof_shared"], :])                      # Shared_extraction.py:27-40
         d = tmp_path / "Distributed_save" / f"Rank-{q}" / "nB-10-nH-50-Lr-0.0005-filter=150"
         os.makedirs(d, exist_ok=True)
         shutil.copy(os.path.join(GOLDEN, f"model_training_ref_rank{q}.pth"), str(d / "model.pth"))
@@ -403,7 +403,7 @@ def test_pipeline_with_surrogates_trained_by_the_unmodified_reference_script(tmp
                        timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     for q in range(2):
-        got = np.load(str(tmp_path / "Results" / "Dynamics" / f"Modeled_Local-rank-{q}.hdf5.npz"))["Displacement"]
+        got = read_result(tmp_path / "Results" / "Dynamics" / f"Modeled_Local-rank-{q}.hdf5")
         ref = sync[q][:, :T]
         assert bits_equal(got[:, :n_p * n_s], ref[:, :n_p * n_s])               # synchronised warm-up (Online_predictor.py:251-270)
         err_end = np.linalg.norm(got[:, -1] - ref[:, -1]) / np.linalg.norm(ref[:, -1])

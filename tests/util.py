@@ -45,3 +45,22 @@ def bits_equal(a, b):
     a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
     b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
     return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def read_result(path, name="Displacement"):
+    """Dataset `name` of a result file the drivers wrote with h5py.File(path, 'w') (Data_prepare.py:243-246): genuine
+    HDF5 at `path` (real h5py, or the package's hdf5_lite behind the compat stand-in); `<path>.npz` archives of the
+    earlier stand-in are accepted too."""
+    if os.path.isfile(str(path)):
+        import saa_b200  # noqa: F401
+        from saa_b200 import hdf5_lite
+        return hdf5_lite.read_file(str(path))[name]
+    return np.load(str(path) + ".npz")[name]
+
+
+def write_result(path, array, name="Displacement"):
+    """A result file as the drivers write it (genuine HDF5, contiguous float64)."""
+    import saa_b200  # noqa: F401
+    from saa_b200 import hdf5_lite
+    os.makedirs(os.path.dirname(str(path)) or ".", exist_ok=True)
+    hdf5_lite.write_file(str(path), {name: np.asarray(array)})
