@@ -158,7 +158,8 @@ def write_file(path, datasets: dict) -> None:
             f.write(_dataset_header(a, da))
         for a, da in zip(arrays, data_addr):
             f.write(b"\0" * (da - f.tell()))
-            f.write(a.tobytes())
+            if a.nbytes:
+                f.write(memoryview(a.reshape(-1)).cast("B"))                # no copy of the (possibly large) history
         assert f.tell() == eof
 
 
@@ -220,7 +221,7 @@ class _Reader:
         if b[o:o + 4] != b"HEAP":
             raise Hdf5Error(f"{self.path}: local heap expected at {heap_addr}")
         seg = self._at(struct.unpack_from("<Q", b, o + 24)[0])
-        end = b.index(b"\0", seg + off)
+        end = b.find(b"\0", seg + off)
         return b[seg + off:end].decode("utf-8")
 
     def _group_btree(self, addr, heap, out):
@@ -392,10 +393,19 @@ class _Reader:
         return out
 
 
+def _map(path):
+    """The file's bytes without reading them: a read-only memory map (datasets are copied out one by one)."""
+    import mmap
+    with open(path, "rb") as f:
+        try:
+            return mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:                                                  # empty file
+            return b""
+
+
 def read_file(path) -> dict:
     """name -> array of every dataset in the root group of an HDF5 file."""
-    with open(path, "rb") as f:
-        r = _Reader(f.read(), str(path))
+    r = _Reader(_map(path), str(path))
     out = {}
     for name, addr in r.members().items():
         try:
@@ -415,8 +425,7 @@ class File:
         self._d, self._reader, self._addr = {}, None, {}
         if mode in ("r", "r+", "a"):
             try:
-                with open(self.filename, "rb") as f:
-                    self._reader = _Reader(f.read(), self.filename)
+                self._reader = _Reader(_map(self.filename), self.filename)
                 self._addr = self._reader.members()
             except FileNotFoundError:
                 if mode != "a":
